@@ -1,0 +1,187 @@
+/*
+ * vtoonify_b200.h — C-ABI of libvtoonify_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for the VToonify per-frame StyleGAN2 synthesis hot path.
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream
+ * handle (`void*` == cudaStream_t) and returns 0 on success / non-zero on error (message via
+ * vt_last_error()).  The library never allocates or frees user-visible memory: outputs and
+ * workspaces are caller-allocated.  All pointers are DEVICE pointers unless noted.  There is no
+ * CPU fallback anywhere in this library.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo williamyang1991/VToonify):
+ *   vt_upfirdn2d_f32        <- pybind `upfirdn2d(input,kernel,up_x,up_y,down_x,down_y,pad_x0,pad_x1,pad_y0,pad_y1)`
+ *                              model/stylegan/op/upfirdn2d.cpp:17-31, upfirdn2d_kernel.cu:209-369
+ *   vt_fused_bias_act_f32   <- pybind `fused_bias_act(input,bias,refer,act,grad,alpha,scale)` (act=3, grad=0)
+ *                              model/stylegan/op/fused_bias_act.cpp:18-32, fused_bias_act_kernel.cu:18-105
+ *   vt_conv2d_*             <- conv2d_gradfix.conv2d / conv_transpose2d (cuDNN via F.conv2d)
+ *                              model/stylegan/op/conv2d_gradfix.py:22-75, and nn.Conv2d at model/vtoonify.py:96-97,111-113,162-182,195-198
+ *   vt_modulate_weights_f32 <- ModulatedConv2d weight modulation/demodulation, model/stylegan/model.py:259-267
+ *   vt_linear_f32           <- EqualLinear.forward (F.linear [+ fused_leaky_relu]), model/stylegan/model.py:153-162
+ *   vt_instnorm_stats_nhwc / vt_adain_apply_nhwc <- AdaptiveInstanceNorm.forward, model/dualstylegan.py:16-21
+ *   vt_fir_nhwc_f32         <- Blur.forward after the transposed conv + NoiseInjection + FusedLeakyReLU,
+ *                              model/stylegan/model.py:74-90, 285, 315-320, 364-370
+ *   vt_smalln_conv_f32      <- ToRGB / fusion_skip / Fusion.conv2 / encoder[-1] (Cout<=4 convs) + Upsample(skip) add,
+ *                              model/stylegan/model.py:383-392, model/vtoonify.py:113,124-127,182,198
+ *   vt_frame_u8_to_f32 / vt_f32_to_frame_u8 <- transforms.ToTensor+Normalize and util.tensor2cv2,
+ *                              style_transfer.py:57-60,160, util.py:190-192
+ */
+#ifndef VTOONIFY_B200_H_
+#define VTOONIFY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+/* ---- library info / errors ------------------------------------------------------------- */
+int         vt_abi_version(void);
+const char* vt_last_error(void);          /* thread-local message of the last failing call   */
+const char* vt_build_info(void);          /* "sm_100a ... " build string                       */
+/* number of kernel launches issued by this library since process start (all threads)        */
+int64_t     vt_launch_count(void);
+
+/* ---- a1: upfirdn2d (planar / NCHW, any up/down/pad/kernel; index-exact) ------------------ */
+/* in : [planes, in_h, in_w] fp32, out: [planes, out_h, out_w] fp32 with
+ * out_h = (in_h*up_y + pad_y0 + pad_y1 - kh + down_y) / down_y   (same for w).
+ * kernel: [kh, kw] fp32 (device). The kernel is flipped (true convolution), negative pads crop. */
+int vt_upfirdn2d_out_size(int in_h, int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                          int pad_x0, int pad_x1, int pad_y0, int pad_y1, int* out_h, int* out_w);
+int vt_upfirdn2d_f32(const float* in, const float* kernel, float* out, int64_t planes, int in_h, int in_w,
+                     int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                     int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* ---- a2: fused bias + leaky-relu + gain (any layout; bias broadcast on dim 1) ------------ */
+/* out[i] = lrelu(in[i] + bias[(i / step_b) % size_b], negative_slope) * scale; bias may be NULL. */
+int vt_fused_bias_act_f32(const float* in, const float* bias, float* out, int64_t n, int64_t step_b,
+                          int size_b, float negative_slope, float scale, void* stream);
+
+/* ---- layout transforms (API boundary NCHW <-> internal NHWC) ------------------------------ */
+/* out NHWC has `c_pad` >= C channels per pixel, the tail is zero-filled. round_tf32: cvt.rna.   */
+int vt_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, int c_pad, int round_tf32, void* stream);
+int vt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, int c_stride, void* stream);
+
+/* ---- a8: EqualLinear ---------------------------------------------------------------------- */
+/* out[r, o] = act( sum_i in[r,i] * (W[o,i]*w_scale) + bias[o]*b_scale ), act: 0 none, 1 lrelu(0.2)*sqrt2 (fused_lrelu),
+ * 2 lrelu(0.2) (nn.LeakyReLU) */
+int vt_linear_f32(const float* in, const float* weight, const float* bias, float* out, int rows, int in_dim,
+                  int out_dim, float w_scale, float b_scale, int act, void* stream);
+
+/* PixelNorm (model/stylegan/model.py:13-18): out[r,:] = in[r,:] * rsqrt(mean(in[r,:]^2) + 1e-8) */
+int vt_pixelnorm_f32(const float* in, float* out, int rows, int dim, void* stream);
+
+/* ---- a3: weight modulation / demodulation and re-layout ---------------------------------- */
+/* W: [Cout, Cin, kh, kw] fp32. style: [wB, Cin] (NULL => ones, wB must be 1). out: [wB][kh*kw][Cout][cin_pad]
+ * out[b][t][n][c] = (scale*W[n][c][t]) * style[b][c] * demod[b][n], demod = rsqrt(sum_{c,t}(.)^2 + 1e-8) if demodulate.
+ * pad channels [Cin, cin_pad) are zero. round_tf32 rounds to TF32 (rna) for the tensor-core path. */
+int vt_modulate_weights_f32(const float* W, const float* style, float* out, int wB, int Cout, int Cin, int kh, int kw,
+                            int cin_pad, float scale, int demodulate, int round_tf32, void* stream);
+
+/* ---- convolution descriptor (NHWC activations) -------------------------------------------- */
+#define VT_MAX_TAPS 9
+#define VT_ACT_NONE 0
+#define VT_ACT_LRELU 1      /* lrelu(slope) * gain                                             */
+#define VT_ACT_RELU_TANH 2  /* tanh(relu(v))      (Fusion mask, model/vtoonify.py:126)          */
+
+typedef struct vt_conv_desc {
+  int32_t struct_size;          /* sizeof(vt_conv_desc), ABI check                               */
+  int32_t n_src;                /* 1 or 2: virtual channel concat of sources                     */
+  const float* src[2];          /* NHWC [B, H, W, src_cstride[i]]                                */
+  int32_t src_c[2];             /* logical channels taken from each source                      */
+  int32_t src_cstride[2];       /* floats per pixel in memory (>= src_c)                         */
+  int32_t B, H, W;              /* input batch / spatial                                         */
+  int32_t Ho, Wo;               /* output spatial (of this call / phase)                         */
+  int32_t stride;               /* in_y = oy*stride + tap_dy[t]                                  */
+  int32_t taps;                 /* number of taps used by this call (<= 9)                       */
+  int32_t tap_dy[VT_MAX_TAPS];
+  int32_t tap_dx[VT_MAX_TAPS];
+  int32_t tap_w[VT_MAX_TAPS];   /* index of the weight slab used by tap t                        */
+  const float* weight;          /* [wB][w_taps][Cout][w_cstride]; channel order = src0 then src1 */
+  int32_t wB;                   /* 1 (shared) or B (per-sample, modulated)                       */
+  int32_t w_taps;               /* slabs per sample in `weight`                                  */
+  int32_t w_cstride;            /* floats per (tap, cout) row (>= src_c[0]+src_c[1])             */
+  int32_t Cout;
+  float*  out;                  /* strided NHWC view: out[b*out_sb + oy*out_sy + ox*out_sx + n]  */
+  int64_t out_sb, out_sy, out_sx;   /* element strides                                           */
+  /* epilogue: v = acc + bias[n] + noise_w[0]*noise[b,oy,ox]; v = act(v); v = v*alpha + beta*res */
+  const float* bias;            /* [Cout] or NULL                                                */
+  const float* noise;           /* [B, Ho, Wo] planar or NULL                                    */
+  const float* noise_w;         /* device scalar or NULL                                         */
+  int32_t act;                  /* VT_ACT_*                                                      */
+  float   slope, gain;          /* lrelu params                                                  */
+  const float* res;             /* residual with the same strided view as out, or NULL          */
+  float   alpha, beta;
+  int32_t round_tf32;           /* round outputs to TF32 (rna) for a tensor-core consumer       */
+  int32_t reserved;
+} vt_conv_desc;
+
+/* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */
+int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream);
+/* tcgen05 (TF32, fp32 accumulate in TMEM), TMA-staged tiles. Requires channel strides % 32 == 0,
+ * Cout % 16 == 0, 16B-aligned views. */
+int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream);
+int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 accepts the descriptor */
+/* tuning knobs for experiments: key in {"tc_mode"}; returns previous value */
+int vt_set_option(const char* key, int value);
+
+/* ---- small-N conv (Cout <= 4): planar output, optional planar extra source + skip upsample */
+typedef struct vt_smalln_desc {
+  int32_t struct_size;
+  int32_t n_planar;             /* 0 or number of leading planar channels (<=4), e.g. skip (3)   */
+  const float* planar;          /* [B, n_planar, H, W] or NULL                                   */
+  const float* planar_weight;   /* [w_taps][Cout][n_planar] weights of the planar channels       */
+  const float* src;             /* NHWC [B,H,W,src_cstride] (may be NULL if src_c == 0)          */
+  int32_t src_c, src_cstride;
+  const float* src2;            /* optional second NHWC source combined as |src - src2| or src*mul */
+  int32_t src2_mode;            /* 0 none                                                        */
+  int32_t B, H, W;
+  int32_t taps;
+  int32_t tap_dy[VT_MAX_TAPS], tap_dx[VT_MAX_TAPS], tap_w[VT_MAX_TAPS];
+  const float* weight;          /* [wB][w_taps][Cout][w_cstride]: weights of the NHWC source     */
+  int32_t wB, w_taps, w_cstride, Cout;
+  const float* bias;            /* [Cout] or NULL                                                */
+  int32_t act;                  /* VT_ACT_NONE or VT_ACT_RELU_TANH                               */
+  const float* skip;            /* optional [B,Cout,H/2,W/2] planar: out += upfirdn2d(skip, up=2, pad=(2,1), skip_kernel) */
+  const float* skip_kernel;     /* [4,4] device                                                  */
+  float* out;                   /* planar [B, Cout, H, W]                                        */
+  float* mul_out;               /* optional NHWC [B,H,W,mul_c]: mul_src * out[:,0] (f_E * m_E)   */
+  const float* mul_src;
+  int32_t mul_c, round_tf32;
+} vt_smalln_desc;
+int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream);
+
+/* ---- FIR on NHWC (Blur after transposed conv) with fused noise + bias + leaky relu -------- */
+/* in : [B, H, W, C] ; kernel [kh,kw] (device, flipped like upfirdn2d); pad (p0,p1) both axes.
+ * out: [B, Ho, Wo, C], Ho = H + p0 + p1 - kh + 1. v = fir; v += noise_w*noise; v = lrelu(v+bias)*gain if act. */
+int vt_fir_nhwc_f32(const float* in, const float* kernel, float* out, int B, int H, int W, int C, int kh, int kw,
+                    int pad0, int pad1, const float* bias, const float* noise, const float* noise_w, int act,
+                    float slope, float gain, int round_tf32, void* stream);
+
+/* ---- a7: instance-norm statistics + AdaIN apply (NHWC) ------------------------------------ */
+/* mode 0: x = in[b,p,c] (c < C). mode 1: virtual cat(in, |in - in2|) with 2C channels.
+ * stats: [B, Cs, 2] = (mean, rstd) with biased variance, eps inside rsqrt; ws: >= B*Cs*2 doubles, zeroed by the call */
+int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
+                           float eps, float* stats, double* ws, void* stream);
+/* out[b,p,c] = gamma[b,c] * (x - mean) * rstd + beta[b,c]; gamma_beta: [B, 2*Cs] (gamma then beta) */
+int vt_adain_apply_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
+                        const float* stats, const float* gamma_beta, float* out, int round_tf32, void* stream);
+
+/* ---- elementwise helpers ------------------------------------------------------------------ */
+/* out = a * scale_a + b * scale_b (b may be NULL) */
+int vt_axpby_f32(const float* a, const float* b, float* out, int64_t n, float scale_a, float scale_b, int round_tf32, void* stream);
+
+/* ---- a11: frame loop transforms ----------------------------------------------------------- */
+/* u8 HWC (RGB or BGR) -> fp32 NCHW in [-1,1]: (v/255 - 0.5)/0.5 ; style_transfer.py:57-60,110,160 */
+int vt_frame_u8_to_f32(const uint8_t* in, float* out, int B, int H, int W, int swap_rb, int64_t out_batch_stride, void* stream);
+/* fp32 NCHW (3ch) -> clamp(-1,1) -> ((v+1)*127.5) truncated to u8, HWC, optional RGB->BGR ; util.py:190-192 */
+int vt_f32_to_frame_u8(const float* in, uint8_t* out, int B, int H, int W, int swap_rb, void* stream);
+
+/* ---- tcgen05/TMA self-test kernels (used by tests/ only; tiny GEMMs that validate descriptors) */
+int vt_selftest_tc_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTOONIFY_B200_H_ */

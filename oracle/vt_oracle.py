@@ -1,0 +1,258 @@
+"""oracle/vt_oracle.py — CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import
+this file, and only as the checker (or as the timed CPU baseline); nothing under ``vtoonify_b200/`` imports it.
+
+It is a functional, state_dict-driven restatement in fp32 on CPU (torch CPU tensors; the dense contractions go through
+``F.conv2d`` / ``F.conv_transpose2d`` / ``F.linear`` exactly where the reference calls them — SURVEY.md §8c: the conv
+arithmetic of the reference itself lives in PyTorch/ATen).  Each function cites the reference lines it follows.
+
+Parity pinning: the reference has no tests or golden vectors, so this oracle is pinned against outputs
+of the reference's own code (``model/stylegan/op_cpu`` path, imported unmodified in the build container) stored under
+``tests/golden/`` by ``tests/golden/make_golden.py``; ``tests/test_oracle_golden.py`` checks every fixture.
+"""
+import math
+import re
+
+import torch
+import torch.nn.functional as F
+
+SQRT2 = math.sqrt(2.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1: upfirdn2d   (model/stylegan/op_cpu/upfirdn2d.py:7-60; CUDA op upfirdn2d_kernel.cu:49-105)
+# ------------------------------------------------------------------------------------------------
+def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0)):
+    """Direct tap-by-tap evaluation (no conv call): zero-stuff, pad / crop, correlate with the flipped kernel,
+    decimate.  Integer index semantics identical to the reference."""
+    up_x, up_y = (up, up) if isinstance(up, int) else up
+    down_x, down_y = (down, down) if isinstance(down, int) else down
+    if len(pad) == 2:
+        pad = (pad[0], pad[1], pad[0], pad[1])
+    px0, px1, py0, py1 = pad
+    B, C, H, W = x.shape
+    kh, kw = kernel.shape
+    # zero-stuffing
+    u = x.new_zeros((B, C, H * up_y, W * up_x))
+    u[:, :, ::up_y, ::up_x] = x
+    # positive pad, then negative pad == crop (op_cpu/upfirdn2d.py:33-41)
+    u = F.pad(u, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
+    u = u[:, :, max(-py0, 0): u.shape[2] - max(-py1, 0), max(-px0, 0): u.shape[3] - max(-px1, 0)]
+    full_h = H * up_y + py0 + py1 - kh + 1
+    full_w = W * up_x + px0 + px1 - kw + 1
+    out_h = (H * up_y + py0 + py1 - kh + down_y) // down_y
+    out_w = (W * up_x + px0 + px1 - kw + down_x) // down_x
+    kf = torch.flip(kernel, [0, 1])
+    acc = x.new_zeros((B, C, full_h, full_w))
+    for ky in range(kh):
+        for kx in range(kw):
+            acc += kf[ky, kx] * u[:, :, ky: ky + full_h, kx: kx + full_w]
+    out = acc[:, :, ::down_y, ::down_x]
+    assert out.shape[2] == out_h and out.shape[3] == out_w
+    return out.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# a2: fused bias + leaky relu   (model/stylegan/op_cpu/fused_act.py:23-34)
+# ------------------------------------------------------------------------------------------------
+def fused_leaky_relu(x, bias=None, negative_slope=0.2, scale=SQRT2):
+    if bias is not None:
+        x = x + bias.view(1, -1, *([1] * (x.ndim - 2)))
+    return F.leaky_relu(x, negative_slope) * scale
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: EqualLinear   (model/stylegan/model.py:133-162)
+# ------------------------------------------------------------------------------------------------
+def equal_linear(x, weight, bias, lr_mul=1.0, activation=False):
+    scale = (1 / math.sqrt(weight.shape[1])) * lr_mul
+    if activation:
+        return fused_leaky_relu(F.linear(x, weight * scale), bias * lr_mul)
+    return F.linear(x, weight * scale, bias=bias * lr_mul)
+
+
+def pixel_norm(x):  # model/stylegan/model.py:13-18
+    return x * torch.rsqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-8)
+
+
+def make_kernel(k):  # model/stylegan/model.py:21-29
+    k = torch.tensor(k, dtype=torch.float32)
+    if k.ndim == 1:
+        k = k[None, :] * k[:, None]
+    return k / k.sum()
+
+
+# ------------------------------------------------------------------------------------------------
+# a3: ModulatedConv2d   (model/stylegan/model.py:227-306).  Restated in the "un-fused" algebra (model.py:230-257):
+#     conv(x * s, scale*W) * d  with  d = rsqrt(sum((scale*W*s)^2) + 1e-8)  — one shared-weight conv per batch.
+# ------------------------------------------------------------------------------------------------
+def modulated_conv2d(x, style, sd, prefix, demodulate=True, upsample=False, downsample=False):
+    W = sd[prefix + "weight"][0]                       # [Cout, Cin, k, k]
+    Cout, Cin, k, _ = W.shape
+    scale = 1 / math.sqrt(Cin * k * k)
+    s = equal_linear(style, sd[prefix + "modulation.weight"], sd[prefix + "modulation.bias"])  # [B, Cin]
+    w = scale * W
+    B = x.shape[0]
+    xs = x * s.view(B, Cin, 1, 1)
+    if upsample:
+        out = F.conv_transpose2d(xs, w.transpose(0, 1), padding=0, stride=2)
+        kern = sd[prefix + "blur.kernel"]
+        p = (kern.shape[0] - 2) - (k - 1)
+        out = upfirdn2d(out, kern, pad=((p + 1) // 2 + 1, p // 2 + 1))
+    elif downsample:
+        kern = sd[prefix + "blur.kernel"]
+        p = (kern.shape[0] - 2) + (k - 1)
+        out = F.conv2d(upfirdn2d(xs, kern, pad=((p + 1) // 2, p // 2)), w, padding=0, stride=2)
+    else:
+        out = F.conv2d(xs, w, padding=k // 2)
+    if demodulate:
+        d = torch.rsqrt((w.unsqueeze(0) * s.view(B, 1, Cin, 1, 1)).square().sum((2, 3, 4)) + 1e-8)
+        out = out * d.view(B, Cout, 1, 1)
+    return out
+
+
+def styled_conv(x, style, sd, prefix, noise=None, upsample=False):
+    """model/stylegan/model.py:364-370: conv -> + noise_weight*noise -> FusedLeakyReLU."""
+    out = modulated_conv2d(x, style, sd, prefix + "conv.", upsample=upsample)
+    if noise is not None:
+        out = out + sd[prefix + "noise.weight"] * noise
+    return fused_leaky_relu(out, sd[prefix + "activate.bias"])
+
+
+def to_rgb(x, style, sd, prefix, skip=None):
+    """model/stylegan/model.py:383-392."""
+    out = modulated_conv2d(x, style, sd, prefix + "conv.", demodulate=False) + sd[prefix + "bias"]
+    if skip is not None:
+        out = out + upfirdn2d(skip, sd[prefix + "upsample.kernel"], up=2, pad=(2, 1))
+    return out
+
+
+def generator_forward(sd, latent, noises, prefix="", log_size=None):
+    """model/stylegan/model.py:566-590 with input_is_latent=True and explicit noise list."""
+    B = latent.shape[0]
+    out = sd[prefix + "input.input"].repeat(B, 1, 1, 1)
+    out = styled_conv(out, latent[:, 0], sd, prefix + "conv1.", noises[0])
+    skip = to_rgb(out, latent[:, 1], sd, prefix + "to_rgb1.")
+    n_levels = len([k for k in sd if re.fullmatch(re.escape(prefix) + r"to_rgbs\.\d+\.bias", k)])
+    i = 1
+    for lv in range(n_levels):
+        out = styled_conv(out, latent[:, i], sd, f"{prefix}convs.{2 * lv}.", noises[1 + 2 * lv], upsample=True)
+        out = styled_conv(out, latent[:, i + 1], sd, f"{prefix}convs.{2 * lv + 1}.", noises[2 + 2 * lv])
+        skip = to_rgb(out, latent[:, i + 2], sd, f"{prefix}to_rgbs.{lv}.", skip)
+        i += 2
+    return skip
+
+
+# ------------------------------------------------------------------------------------------------
+# a7: AdaIN / AdaResBlock   (model/dualstylegan.py:6-45)
+# ------------------------------------------------------------------------------------------------
+def adain(x, style, sd, prefix):
+    gb = F.linear(style, sd[prefix + "style.weight"], sd[prefix + "style.bias"]).unsqueeze(2).unsqueeze(3)
+    gamma, beta = gb.chunk(2, 1)
+    return gamma * F.instance_norm(x, eps=1e-5) + beta
+
+
+def conv_layer(x, sd, prefix, dilation=1):
+    """ConvLayer = EqualConv2d(no bias) + FusedLeakyReLU(bias)  (model/stylegan/model.py:593-637)."""
+    W = sd[prefix + "0.weight"]
+    scale = 1 / math.sqrt(W.shape[1] * W.shape[2] ** 2)
+    out = F.conv2d(x, W * scale, padding=W.shape[2] // 2 + dilation - 1, dilation=dilation)
+    return fused_leaky_relu(out, sd[prefix + "1.bias"])
+
+
+def ada_res_block(x, s, w, sd, prefix, dilation):
+    if w == 0:
+        return x
+    out = conv_layer(adain(x, s, sd, prefix + "norm."), sd, prefix + "conv.", dilation)
+    out = conv_layer(adain(out, s, sd, prefix + "norm2."), sd, prefix + "conv2.", dilation)
+    return out * w + x
+
+
+# ------------------------------------------------------------------------------------------------
+# a6: VToonify.forward   (model/vtoonify.py:210-277)
+# ------------------------------------------------------------------------------------------------
+def vtoonify_forward(sd, x, style, d_s=None, backbone="dualstylegan", in_size=256, return_mask=False):
+    D = backbone == "dualstylegan"
+    gp = "generator.generator." if D else "generator."
+    n_latent = 18
+    # styles (:212-224)
+    if style.ndim < 3:
+        style = style.unsqueeze(1).repeat(1, n_latent, 1)
+    nB, nL, nD = style.shape
+    adastyles = style
+    if D:
+        t = pixel_norm(style.reshape(nB * nL, nD))
+        for i in (1, 2):
+            t = equal_linear(t, sd[f"generator.style.{i}.weight"], sd[f"generator.style.{i}.bias"], 0.01, True)
+        resstyles = t.reshape(nB, nL, nD)
+        adastyles = adastyles.clone()
+        for i in range(7, n_latent):
+            adastyles[:, i] = equal_linear(adastyles[:, i], sd[f"generator.res.{i}.weight"], sd[f"generator.res.{i}.bias"])
+
+    def conv(t, key, stride=1, padding=1):
+        return F.conv2d(t, sd[key + ".weight"], sd[key + ".bias"], stride=stride, padding=padding)
+
+    # encoder (:160-176, :230-242)
+    n_blocks = int(math.log2(in_size)) - 4          # 4 for in_size 256
+    feat = x
+    feats = []
+    for bi in range(n_blocks):
+        feat = F.leaky_relu(conv(feat, f"encoder.{bi}.0", stride=1 if bi == 0 else 2), 0.2)
+        feat = F.leaky_relu(conv(feat, f"encoder.{bi}.2"), 0.2)
+        feats.append(feat)
+    feats = feats[::-1]
+    dil = {1: 4, 2: 4, 3: 2, 4: 2, 5: 1, 6: 1}
+    for ii in range(6):
+        p = f"encoder.{n_blocks}.{ii}."
+        out = F.leaky_relu(conv(feat, p + "conv"), 0.2)
+        out = F.leaky_relu(conv(out, p + "conv2"), 0.2)
+        feat = (out + feat) / math.sqrt(2)
+        if D:
+            feat = ada_res_block(feat, resstyles[:, ii + 1], d_s, sd, f"res.{ii + 1}.", dil[ii + 1])
+    out = feat
+    skip = conv(feat, f"encoder.{n_blocks + 1}", padding=0)
+
+    # generator tail with fusion (:249-272)
+    m_Es = []
+    idx = 1
+    for lv in range(5):
+        if 2 ** (5 + ((idx - 1) // 2)) <= in_size:
+            fi = (idx - 1) // 2
+            f_E = feats[fi]
+            if D:
+                fp = f"fusion_out.{fi}."
+                label = torch.zeros(out.shape[0], 1) + d_s
+                label = F.leaky_relu(F.linear(label, sd[fp + "linear.0.weight"], sd[fp + "linear.0.bias"]), 0.2)
+                label = F.leaky_relu(F.linear(label, sd[fp + "linear.2.weight"], sd[fp + "linear.2.bias"]), 0.2)
+                cat = torch.cat([out, (out - f_E).abs()], dim=1)
+                m_E = torch.tanh(F.relu(conv(adain(cat, label, sd, fp + "norm."), fp + "conv2")))
+                out = conv(torch.cat([out, f_E * m_E], dim=1), fp + "conv")
+                skip = conv(torch.cat([skip, f_E * m_E], dim=1), f"fusion_skip.{fi}")
+                m_Es.append(m_E)
+            else:
+                out = conv(torch.cat([out, f_E], dim=1), f"fusion_out.{fi}")
+                skip = conv(torch.cat([skip, f_E], dim=1), f"fusion_skip.{fi}")
+        # noise is all-zero in the reference (:266-267), i.e. absent
+        out = styled_conv(out, adastyles[:, idx + 6], sd, f"{gp}convs.{6 + 2 * lv}.", None, upsample=True)
+        out = styled_conv(out, adastyles[:, idx + 7], sd, f"{gp}convs.{7 + 2 * lv}.", None)
+        skip = to_rgb(out, adastyles[:, idx + 8], sd, f"{gp}to_rgbs.{3 + lv}.", skip)
+        idx += 2
+    if return_mask and D:
+        return skip, m_Es
+    return skip
+
+
+# ------------------------------------------------------------------------------------------------
+# a11: frame transforms   (style_transfer.py:57-60,160; util.py:190-192)
+# ------------------------------------------------------------------------------------------------
+def frame_u8_to_f32(frames_u8):
+    """uint8 [B,H,W,3] -> fp32 [B,3,H,W]: ToTensor (v/255) then Normalize(0.5, 0.5)."""
+    t = frames_u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
+    return (t - 0.5) / 0.5
+
+
+def tensor2frame_u8(img, swap_rb=True):
+    """clamp(-1,1) (style_transfer.py:177) then util.tensor2cv2: ((x+1)*127.5).astype(uint8), RGB->BGR."""
+    t = ((img.clamp(-1, 1).permute(0, 2, 3, 1) + 1.0) * 127.5).to(torch.uint8)  # truncation like numpy astype
+    return t.flip(-1) if swap_rb else t

@@ -1,0 +1,112 @@
+"""ctypes binding of libvtoonify_b200.so (the C-ABI declared in include/vtoonify_b200.h).
+
+The product path fails loudly when the CUDA extension is missing: there is no CPU or PyTorch
+fallback behind these calls.  The library is built in-tree by ``__graft_entry__.build()`` /
+``vtoonify_b200/csrc/build.sh`` into ``vtoonify_b200/lib/``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvtoonify_b200.so")
+VT_MAX_TAPS = 9
+ACT_NONE, ACT_LRELU, ACT_RELU_TANH = 0, 1, 2
+
+
+class VtError(RuntimeError):
+    pass
+
+
+class ConvDesc(Structure):
+    _fields_ = [
+        ("struct_size", c_int32), ("n_src", c_int32),
+        ("src", c_void_p * 2), ("src_c", c_int32 * 2), ("src_cstride", c_int32 * 2),
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("Ho", c_int32), ("Wo", c_int32),
+        ("stride", c_int32), ("taps", c_int32),
+        ("tap_dy", c_int32 * VT_MAX_TAPS), ("tap_dx", c_int32 * VT_MAX_TAPS), ("tap_w", c_int32 * VT_MAX_TAPS),
+        ("weight", c_void_p), ("wB", c_int32), ("w_taps", c_int32), ("w_cstride", c_int32), ("Cout", c_int32),
+        ("out", c_void_p), ("out_sb", c_int64), ("out_sy", c_int64), ("out_sx", c_int64),
+        ("bias", c_void_p), ("noise", c_void_p), ("noise_w", c_void_p),
+        ("act", c_int32), ("slope", c_float), ("gain", c_float),
+        ("res", c_void_p), ("alpha", c_float), ("beta", c_float),
+        ("round_tf32", c_int32), ("reserved", c_int32),
+    ]
+
+
+class SmallNDesc(Structure):
+    _fields_ = [
+        ("struct_size", c_int32), ("n_planar", c_int32),
+        ("planar", c_void_p), ("planar_weight", c_void_p),
+        ("src", c_void_p), ("src_c", c_int32), ("src_cstride", c_int32),
+        ("src2", c_void_p), ("src2_mode", c_int32),
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("taps", c_int32),
+        ("tap_dy", c_int32 * VT_MAX_TAPS), ("tap_dx", c_int32 * VT_MAX_TAPS), ("tap_w", c_int32 * VT_MAX_TAPS),
+        ("weight", c_void_p), ("wB", c_int32), ("w_taps", c_int32), ("w_cstride", c_int32), ("Cout", c_int32),
+        ("bias", c_void_p), ("act", c_int32),
+        ("skip", c_void_p), ("skip_kernel", c_void_p),
+        ("out", c_void_p), ("mul_out", c_void_p), ("mul_src", c_void_p),
+        ("mul_c", c_int32), ("round_tf32", c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/vtoonify_b200.h declares
+_P = c_void_p
+SYMBOLS = {
+    "vt_abi_version": (c_int, []),
+    "vt_last_error": (c_char_p, []),
+    "vt_build_info": (c_char_p, []),
+    "vt_launch_count": (c_int64, []),
+    "vt_upfirdn2d_out_size": (c_int, [c_int] * 12 + [POINTER(c_int), POINTER(c_int)]),
+    "vt_upfirdn2d_f32": (c_int, [_P, _P, _P, c_int64] + [c_int] * 12 + [_P]),
+    "vt_fused_bias_act_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P]),
+    "vt_nchw_to_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "vt_nhwc_to_nchw_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "vt_linear_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_int, _P]),
+    "vt_pixelnorm_f32": (c_int, [_P, _P, c_int, c_int, _P]),
+    "vt_modulate_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
+    "vt_conv2d_direct_f32": (c_int, [POINTER(ConvDesc), _P]),
+    "vt_conv2d_tc_tf32": (c_int, [POINTER(ConvDesc), _P]),
+    "vt_conv2d_tc_supported": (c_int, [POINTER(ConvDesc)]),
+    "vt_set_option": (c_int, [c_char_p, c_int]),
+    "vt_smalln_conv_f32": (c_int, [POINTER(SmallNDesc), _P]),
+    "vt_fir_nhwc_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int,
+                                c_float, c_float, c_int, _P]),
+    "vt_instnorm_stats_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "vt_adain_apply_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, _P, _P, _P, c_int, _P]),
+    "vt_axpby_f32": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_int, _P]),
+    "vt_frame_u8_to_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
+    "vt_f32_to_frame_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "vt_selftest_tc_gemm": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every declared symbol. Raises VtError if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VtError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or vtoonify_b200/csrc/build.sh). vtoonify_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vt_abi_version() != 1:
+        raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise VtError(load().vt_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().vt_launch_count())

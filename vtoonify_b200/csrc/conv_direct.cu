@@ -1,0 +1,331 @@
+// conv_direct.cu — fp32-exact CUDA-core convolutions on NHWC activations.
+//
+//   vt_conv2d_direct_f32 : implicit-GEMM FFMA kernel (64 pixels x 64 couts x 16 k per CTA, 4x4 register tile).
+//                          It is the fp32 reference-grade path ("precision=fp32") used to cross-check the tcgen05
+//                          kernel on the GPU and to run shapes the tensor-core kernel does not take.
+//   vt_smalln_conv_f32   : Cout <= 4 convolutions (ToRGB 1x1, fusion_skip 3x3, Fusion mask 3x3, encoder[-1] 1x1).
+//                          These are < 0.4 % of the FLOPs but read the largest tensors, so they
+//                          are written as HBM-streaming kernels: 8 lanes x float4 cover 32 channels of one pixel,
+//                          weights live in shared memory, planar (NCHW) 3-channel output, with the skip-path
+//                          `Upsample` (upfirdn2d up=2, model/stylegan/model.py:32-50,388-390) and the
+//                          `f_E * m_E` product (model/vtoonify.py:127) fused into the epilogue.
+//
+// Both follow the arithmetic of F.conv2d / F.conv_transpose2d as called by the reference at
+// model/stylegan/op/conv2d_gradfix.py:34-42,66-75 and model/vtoonify.py:96-97,111-113,162-182,195-198:
+// a transposed stride-2 conv is issued as 4 polyphase calls (tap lists with dy,dx in {0,-1}) into a strided view.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int LDA = BM + 4, LDB = BN + 4;
+
+struct DirectArgs {
+  vt_conv_desc d;
+};
+
+__global__ void __launch_bounds__(256)
+conv_direct_kernel(const __grid_constant__ DirectArgs args) {
+  const vt_conv_desc& d = args.d;
+  __shared__ __align__(16) float As[BK][LDA];
+  __shared__ __align__(16) float Bs[BK][LDB];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.y * BN;
+  const int64_t HoWo = (int64_t)d.Ho * d.Wo;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int wb = (d.wB > 1) ? b : 0;
+
+  // loader role
+  const int lp = tid >> 2;        // pixel (A) / cout (B) index within the tile
+  const int lk = (tid & 3) * 4;   // k offset within the chunk
+  const int64_t lm = m0 + lp;
+  const bool lm_ok = lm < HoWo;
+  const int loy = lm_ok ? (int)(lm / d.Wo) : 0;
+  const int lox = lm_ok ? (int)(lm % d.Wo) : 0;
+  const int ln = n0 + lp;
+  const bool ln_ok = ln < d.Cout;
+
+  // compute role
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int coff = 0;
+  for (int s = 0; s < d.n_src; ++s) {
+    const float* sp = d.src[s];
+    const int sc = d.src_c[s], scs = d.src_cstride[s];
+    for (int t = 0; t < d.taps; ++t) {
+      const int iy = loy * d.stride + d.tap_dy[t];
+      const int ix = lox * d.stride + d.tap_dx[t];
+      const bool pix_ok = lm_ok && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+      const float* ap = sp + (((int64_t)b * d.H + iy) * d.W + ix) * scs;
+      const float* wp = d.weight + (((int64_t)wb * d.w_taps + d.tap_w[t]) * d.Cout + ln) * d.w_cstride + coff;
+      for (int c0 = 0; c0 < sc; c0 += BK) {
+        const int c = c0 + lk;
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pix_ok && c < sc) av = *reinterpret_cast<const float4*>(ap + c);
+        if (ln_ok && c < sc) bv = *reinterpret_cast<const float4*>(wp + c);
+        __syncthreads();  // previous chunk fully consumed
+        As[lk + 0][lp] = av.x; As[lk + 1][lp] = av.y; As[lk + 2][lp] = av.z; As[lk + 3][lp] = av.w;
+        Bs[lk + 0][lp] = bv.x; Bs[lk + 1][lp] = bv.y; Bs[lk + 2][lp] = bv.z; Bs[lk + 3][lp] = bv.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+      }
+    }
+    coff += sc;
+  }
+
+  // epilogue
+  const float nw = (d.noise && d.noise_w) ? *d.noise_w : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= HoWo) continue;
+    const int oy = (int)(m / d.Wo), ox = (int)(m % d.Wo);
+    const int64_t off = (int64_t)b * d.out_sb + (int64_t)oy * d.out_sy + (int64_t)ox * d.out_sx;
+    const float nz = d.noise ? nw * d.noise[(int64_t)b * HoWo + m] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= d.Cout) continue;
+      float v = acc[i][j];
+      if (d.noise) v += nz;
+      if (d.bias) v += d.bias[n];
+      if (d.act == VT_ACT_LRELU) v = vt_lrelu(v, d.slope) * d.gain;
+      else if (d.act == VT_ACT_RELU_TANH) v = tanhf(fmaxf(v, 0.f));
+      if (d.res) v = v * d.alpha + d.beta * d.res[off + n];
+      else if (d.alpha != 1.f) v = v * d.alpha;
+      if (d.round_tf32) v = vt_round_tf32(v);
+      d.out[off + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SmallNArgs {
+  vt_smalln_desc d;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256)
+smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
+  const vt_smalln_desc& d = args.d;
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                                  // [taps][N][src_c]
+  float* Wp = smem + (size_t)d.taps * N * d.src_c;   // [taps][N][n_planar]
+  float* Ks = Wp + (size_t)d.taps * N * (d.n_planar > 0 ? d.n_planar : 0);  // [16] skip kernel
+  const int b = blockIdx.y;
+  const int wb = d.wB > 1 ? b : 0;
+  for (int i = threadIdx.x; i < d.taps * N * d.src_c; i += blockDim.x) {
+    const int c = i % d.src_c;
+    const int tn = i / d.src_c;
+    const int t = tn / N, n = tn % N;
+    Ws[i] = d.weight[(((int64_t)wb * d.w_taps + d.tap_w[t]) * d.Cout + n) * d.w_cstride + c];
+  }
+  if (d.n_planar > 0) {
+    for (int i = threadIdx.x; i < d.taps * N * d.n_planar; i += blockDim.x) {
+      const int cp = i % d.n_planar;
+      const int tn = i / d.n_planar;
+      const int t = tn / N, n = tn % N;
+      Wp[i] = d.planar_weight[((int64_t)d.tap_w[t] * d.Cout + n) * d.n_planar + cp];
+    }
+  }
+  if (d.skip && threadIdx.x < 16) Ks[threadIdx.x] = d.skip_kernel[threadIdx.x];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;      // channel slice
+  const int grp = lane >> 3;     // pixel within the warp's group of 4
+  const int warp = threadIdx.x >> 5;
+  const int64_t HW = (int64_t)d.H * d.W;
+  const int64_t groups = vt_cdiv(HW, 4);
+  const int hs = d.H / 2, ws = d.W / 2;
+  for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < groups; g += (int64_t)gridDim.x * 8) {
+    const int64_t p = g * 4 + grp;
+    const bool p_ok = p < HW;
+    const int y = p_ok ? (int)(p / d.W) : 0, x = p_ok ? (int)(p % d.W) : 0;
+    float acc[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[n] = 0.f;
+    if (p_ok && d.src_c > 0) {
+      for (int t = 0; t < d.taps; ++t) {
+        const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+        if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+        const float* ap = d.src + (((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride;
+        const float* wt = Ws + (size_t)t * N * d.src_c;
+        for (int c = sub * 4; c < d.src_c; c += 32) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + c);
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + n * d.src_c + c);
+            acc[n] = fmaf(a.x, w.x, acc[n]);
+            acc[n] = fmaf(a.y, w.y, acc[n]);
+            acc[n] = fmaf(a.z, w.z, acc[n]);
+            acc[n] = fmaf(a.w, w.w, acc[n]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+    }
+    float m0v = 0.f;
+    if (p_ok && sub == 0) {
+      if (d.n_planar > 0) {
+        for (int t = 0; t < d.taps; ++t) {
+          const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+          if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+          for (int cp = 0; cp < d.n_planar; ++cp) {
+            const float a = d.planar[((int64_t)b * d.n_planar + cp) * HW + (int64_t)iy * d.W + ix];
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc[n] = fmaf(a, Wp[(t * N + n) * d.n_planar + cp], acc[n]);
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        float v = acc[n];
+        if (d.bias) v += d.bias[n];
+        if (d.act == VT_ACT_RELU_TANH) v = tanhf(fmaxf(v, 0.f));
+        if (d.skip) {
+          // upfirdn2d(skip, k, up=2, down=1, pad=(2,1)) at (y, x): taps with (y - 2 + ky) even
+          const float* sp = d.skip + ((int64_t)b * N + n) * (int64_t)hs * ws;
+          float u = 0.f;
+          const int ty = y - 2, tx = x - 2;
+          for (int ky = (ty & 1) ? 1 : 0; ky < 4; ky += 2) {
+            const int iy = (ty + ky) >> 1;  // ty + ky is even; arithmetic shift == floor
+            if (ty + ky < 0 || iy >= hs) continue;
+            for (int kx = (tx & 1) ? 1 : 0; kx < 4; kx += 2) {
+              const int ix = (tx + kx) >> 1;
+              if (tx + kx < 0 || ix >= ws) continue;
+              u = fmaf(sp[(int64_t)iy * ws + ix], Ks[(3 - ky) * 4 + (3 - kx)], u);
+            }
+          }
+          v += u;
+        }
+        d.out[((int64_t)b * N + n) * HW + p] = v;
+        if (n == 0) m0v = v;
+      }
+    }
+    if (d.mul_out) {
+      m0v = __shfl_sync(0xffffffffu, m0v, grp * 8);
+      if (p_ok) {
+        const float* ms = d.mul_src + ((int64_t)b * HW + p) * d.mul_c;
+        float* mo = d.mul_out + ((int64_t)b * HW + p) * d.mul_c;
+        for (int c = sub * 4; c < d.mul_c; c += 32) {
+          float4 a = *reinterpret_cast<const float4*>(ms + c);
+          a.x *= m0v; a.y *= m0v; a.z *= m0v; a.w *= m0v;
+          if (d.round_tf32) { a.x = vt_round_tf32(a.x); a.y = vt_round_tf32(a.y); a.z = vt_round_tf32(a.z); a.w = vt_round_tf32(a.w); }
+          *reinterpret_cast<float4*>(mo + c) = a;
+        }
+      }
+    }
+  }
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+static int validate_conv_desc(const vt_conv_desc* d, const char* who) {
+  VT_CHECK(d != nullptr, "%s: null descriptor", who);
+  VT_CHECK(d->struct_size == (int)sizeof(vt_conv_desc), "%s: descriptor size mismatch (got %d, want %d)", who,
+           d->struct_size, (int)sizeof(vt_conv_desc));
+  VT_CHECK(d->n_src == 1 || d->n_src == 2, "%s: n_src must be 1 or 2", who);
+  VT_CHECK(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Ho >= 1 && d->Wo >= 1, "%s: bad spatial shape", who);
+  VT_CHECK(d->stride >= 1 && d->taps >= 1 && d->taps <= VT_MAX_TAPS, "%s: bad stride/taps", who);
+  VT_CHECK(d->Cout >= 1 && d->weight && d->out, "%s: bad weight/out", who);
+  VT_CHECK(d->wB == 1 || d->wB == d->B, "%s: wB must be 1 or B", who);
+  int ctot = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    VT_CHECK(d->src[s] != nullptr, "%s: null source %d", who, s);
+    VT_CHECK(d->src_c[s] >= 4 && d->src_c[s] % 4 == 0, "%s: src_c[%d]=%d must be a multiple of 4", who, s, d->src_c[s]);
+    VT_CHECK(d->src_cstride[s] >= d->src_c[s] && d->src_cstride[s] % 4 == 0, "%s: bad channel stride", who);
+    VT_CHECK(aligned16(d->src[s]), "%s: source %d not 16-byte aligned", who, s);
+    ctot += d->src_c[s];
+  }
+  VT_CHECK(d->w_cstride >= ctot && d->w_cstride % 4 == 0 && aligned16(d->weight), "%s: bad weight stride/alignment", who);
+  for (int t = 0; t < d->taps; ++t)
+    VT_CHECK(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "%s: tap_w[%d] out of range", who, t);
+  VT_CHECK(d->act >= 0 && d->act <= 2, "%s: bad act", who);
+  if (d->noise) VT_CHECK(d->noise_w != nullptr, "%s: noise without noise_w", who);
+  return 0;
+}
+int vt_validate_conv_desc(const vt_conv_desc* d, const char* who) { return validate_conv_desc(d, who); }
+
+extern "C" int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream) {
+  if (validate_conv_desc(d, "conv2d_direct")) return 1;
+  VT_CHECK(d->B <= 65535 && vt_cdiv(d->Cout, BN) <= 65535, "conv2d_direct: grid too large");
+  DirectArgs a;
+  a.d = *d;
+  const int64_t HoWo = (int64_t)d->Ho * d->Wo;
+  dim3 grid((unsigned)vt_cdiv(HoWo, BM), (unsigned)vt_cdiv(d->Cout, BN), (unsigned)d->B);
+  conv_direct_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
+  VT_CHECK(d != nullptr, "smalln_conv: null descriptor");
+  VT_CHECK(d->struct_size == (int)sizeof(vt_smalln_desc), "smalln_conv: descriptor size mismatch (got %d, want %d)",
+           d->struct_size, (int)sizeof(vt_smalln_desc));
+  VT_CHECK(d->Cout >= 1 && d->Cout <= 4, "smalln_conv: Cout must be in [1,4]");
+  VT_CHECK(d->B >= 1 && d->B <= 65535 && d->H >= 1 && d->W >= 1, "smalln_conv: bad shape");
+  VT_CHECK(d->taps >= 1 && d->taps <= VT_MAX_TAPS, "smalln_conv: bad taps");
+  VT_CHECK(d->src_c >= 0 && d->src_c % 4 == 0 && d->src_cstride % 4 == 0 && d->src_cstride >= d->src_c, "smalln_conv: src_c must be a multiple of 4");
+  VT_CHECK(d->src_c == 0 || (d->src && aligned16(d->src)), "smalln_conv: bad src pointer");
+  VT_CHECK(d->n_planar >= 0 && d->n_planar <= 4, "smalln_conv: n_planar must be <= 4");
+  VT_CHECK(d->n_planar == 0 || (d->planar && d->planar_weight), "smalln_conv: planar source needs planar weights");
+  VT_CHECK(d->src2_mode == 0, "smalln_conv: src2_mode not supported");
+  VT_CHECK(d->wB == 1 || d->wB == d->B, "smalln_conv: wB must be 1 or B");
+  VT_CHECK(d->weight || d->src_c == 0, "smalln_conv: null weight");
+  VT_CHECK(d->act == VT_ACT_NONE || d->act == VT_ACT_RELU_TANH, "smalln_conv: bad act");
+  VT_CHECK(d->out != nullptr, "smalln_conv: null out");
+  if (d->skip) VT_CHECK(d->skip_kernel && d->H % 2 == 0 && d->W % 2 == 0, "smalln_conv: skip needs a 4x4 kernel and even H, W");
+  if (d->mul_out) VT_CHECK(d->mul_src && d->mul_c % 4 == 0 && aligned16(d->mul_src) && aligned16(d->mul_out), "smalln_conv: bad mul_out args");
+  for (int t = 0; t < d->taps; ++t) VT_CHECK(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "smalln_conv: tap_w out of range");
+
+  SmallNArgs a;
+  a.d = *d;
+  const size_t smem = ((size_t)d->taps * d->Cout * (d->src_c + d->n_planar) + 16) * sizeof(float);
+  VT_CHECK(smem <= 200 * 1024, "smalln_conv: weights (%zu B) do not fit in shared memory", smem);
+  const int64_t HW = (int64_t)d->H * d->W;
+  int64_t blocks = vt_cdiv(vt_cdiv(HW, 4), 8);
+  const int64_t cap = (int64_t)vt_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)d->B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define VT_LAUNCH_SMALLN(NN)                                                                                   \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      VT_CUDA(cudaFuncSetAttribute(smalln_conv_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    smalln_conv_kernel<NN><<<grid, 256, smem, st>>>(a);                                                        \
+  } while (0)
+  switch (d->Cout) {
+    case 1: VT_LAUNCH_SMALLN(1); break;
+    case 2: VT_LAUNCH_SMALLN(2); break;
+    case 3: VT_LAUNCH_SMALLN(3); break;
+    default: VT_LAUNCH_SMALLN(4); break;
+  }
+#undef VT_LAUNCH_SMALLN
+  VT_LAUNCH_CHECK();
+  return 0;
+}

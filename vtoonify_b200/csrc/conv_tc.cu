@@ -1,0 +1,472 @@
+// conv_tc.cu — the hot kernel: NHWC convolution as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[128 pixels, N couts] (TMEM, fp32) += A[128 pixels, 32 ch] (smem, TF32) * W[N couts, 32 ch]^T (smem, TF32)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 (1 lane)  TMA producer : activation tiles are 4-D boxes (32 ch, 8 x, 16 y, 1 b) of the NHWC tensor, shifted by
+//                                   the filter tap; out-of-image pixels are zero-filled by TMA == the conv's zero padding,
+//                                   so there is no im2col buffer and no bounds code.  Weight tiles are (32 ch, N, 1 tap, 1 b)
+//                                   boxes of the per-sample modulated/demodulated weights [b][tap][cout][cin].
+//   warp 1 (1 lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32, M=128, N<=256, K=8 x4 per 128-byte swizzle row,
+//                                   accumulators double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of i+1.
+//   warp 2           TMEM alloc / dealloc
+//   warps 4-7        epilogue     : tcgen05.ld 32 columns at a time -> (+noise, +bias, leaky-relu*gain, residual, TF32 rna) ->
+//                                   128B-swizzled smem staging -> TMA store (clips partial tiles).
+//
+// A-operand reuse ("halo" mode, stride-1 convs): one TMA box of (8+2d) x (16+2d) pixels per 32-channel chunk serves all
+// 9 taps; each tap's MMA reads it through a descriptor whose start address is shifted by whole 128-byte rows and whose
+// stride-byte-offset is the halo row pitch, so the activations cross L2->smem once instead of nine times.
+//
+// The modulated convolution of the reference (model/stylegan/model.py:259-304: per-sample weights + grouped conv) and the
+// plain convs (model/vtoonify.py:96-97,111-113,162-182) are the same GEMM here; a stride-2 transposed conv is 4 polyphase
+// calls, a stride-2 conv reads 4 parity views of the input (see make_views()).
+#include "tc_common.cuh"
+#include <mutex>
+
+using namespace vt_tc;
+
+int vt_validate_conv_desc(const vt_conv_desc* d, const char* who);
+
+namespace {
+
+constexpr int TILE_W = 8, TILE_H = 16, TILE_M = 128;
+constexpr int KCH = 32;                       // fp32 channels per K chunk = one 128-byte swizzle row
+constexpr int STAGING_BYTES = TILE_M * 128;   // one 32-column output chunk
+constexpr int MAX_SMEM = 227 * 1024;
+
+struct TcArgs {
+  CUtensorMap in_map[2][4];
+  CUtensorMap w_map;
+  CUtensorMap out_map;
+  int n_src, kchunks[2], coff[2];
+  int taps, tap_view[VT_MAX_TAPS], tap_vx[VT_MAX_TAPS], tap_vy[VT_MAX_TAPS], tap_w[VT_MAX_TAPS];
+  int halo, halo_x0, halo_y0, halo_w, base_offset_mode;
+  int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes;
+  int block_n, n_tiles, tiles_x, tiles_y, B, total_tiles, tmem_cols;
+  int Ho, Wo, Cout, wB;
+  const float* bias;
+  const float* noise;
+  const float* noise_w;
+  const float* res;
+  int64_t out_sb, out_sy, out_sx;
+  int act, round_tf32;
+  float slope, gain, alpha, beta;
+};
+
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage_bytes;
+  const uint32_t st_base = b_base + (uint32_t)p.b_stages * p.b_stage_bytes;
+  const uint32_t bar_base = st_base + 2 * STAGING_BYTES;
+  // barriers: a_full[8] a_empty[8] b_full[8] b_empty[8] tmem_full[2] tmem_empty[2]
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 64u + 8u * i; };
+  auto b_full = [&](int i) { return bar_base + 128u + 8u * i; };
+  auto b_empty = [&](int i) { return bar_base + 192u + 8u * i; };
+  auto t_full = [&](int i) { return bar_base + 256u + 8u * i; };
+  auto t_empty = [&](int i) { return bar_base + 272u + 8u * i; };
+  const uint32_t tmem_slot = bar_base + 288u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_src; ++s)
+      for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.in_map[s][v]);
+    tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      uint32_t a_it = 0, b_it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / m_tiles, m = tile % m_tiles;
+        const int b = m / tiles_per_img, rem = m % tiles_per_img;
+        const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * TILE_W;
+        const int n0 = n_tile * p.block_n;
+        const int wb = p.wB > 1 ? b : 0;
+        for (int s = 0; s < p.n_src; ++s) {
+          for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+            const int c0 = kc * KCH;
+            if (p.halo) {
+              const int st = a_it % p.a_stages;
+              mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 1);
+              mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
+              tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][0], a_full(st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+              ++a_it;
+            }
+            for (int t = 0; t < p.taps; ++t) {
+              if (!p.halo) {
+                const int st = a_it % p.a_stages;
+                mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 2);
+                mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
+                tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][p.tap_view[t]], a_full(st), c0, ox0 + p.tap_vx[t],
+                            oy0 + p.tap_vy[t], b);
+                ++a_it;
+              }
+              const int st = b_it % p.b_stages;
+              mbar_wait(b_empty(st), ((b_it / p.b_stages) & 1) ^ 1, 3);
+              mbar_arrive_expect_tx(b_full(st), (uint32_t)(p.block_n * 128));
+              tma_load_4d(b_base + st * p.b_stage_bytes, &p.w_map, b_full(st), p.coff[s] + c0, n0, p.tap_w[t], wb);
+              ++b_it;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      const uint32_t idesc = make_idesc_tf32(TILE_M, p.block_n);
+      uint32_t a_it = 0, b_it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        mbar_wait(t_empty(as), ((lt >> 1) & 1) ^ 1, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.n_src; ++s) {
+          for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+            int sta = 0;
+            if (p.halo) {
+              sta = a_it % p.a_stages;
+              mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 5);
+            }
+            for (int t = 0; t < p.taps; ++t) {
+              if (!p.halo) {
+                sta = a_it % p.a_stages;
+                mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 6);
+              }
+              const int stb = b_it % p.b_stages;
+              mbar_wait(b_full(stb), (b_it / p.b_stages) & 1, 7);
+              tc_fence_after();
+              uint32_t a_addr = a_base + sta * p.a_stage_bytes;
+              uint32_t sbo = 1024;
+              uint32_t boff = 0;
+              if (p.halo) {
+                a_addr += (uint32_t)(((p.tap_vy[t] - p.halo_y0) * p.halo_w + (p.tap_vx[t] - p.halo_x0)) * 128);
+                sbo = (uint32_t)p.halo_w * 128u;
+                if (p.base_offset_mode) boff = (a_addr >> 7) & 7u;
+              }
+              const uint64_t adesc = make_smem_desc_sw128(a_addr, sbo, boff);
+              const uint64_t bdesc = make_smem_desc_sw128(b_base + stb * p.b_stage_bytes, 1024, 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(b_empty(stb));
+              ++b_it;
+              if (!p.halo) { umma_commit(a_empty(sta)); ++a_it; }
+            }
+            if (p.halo) { umma_commit(a_empty(sta)); ++a_it; }
+          }
+        }
+        umma_commit(t_full(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;
+    const int r = q * 32 + lane;           // accumulator row == pixel index in the tile
+    const int ty = r / TILE_W, tx = r % TILE_W;
+    const bool store_thread = (threadIdx.x == 128);
+    const float nw = (p.noise && p.noise_w) ? *p.noise_w : 0.f;
+    uint32_t lt = 0, chunk = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int n_tile = tile / m_tiles, m = tile % m_tiles;
+      const int b = m / tiles_per_img, rem = m % tiles_per_img;
+      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * TILE_W;
+      const int n0 = n_tile * p.block_n;
+      const int oy = oy0 + ty, ox = ox0 + tx;
+      const bool in_img = oy < p.Ho && ox < p.Wo;
+      const int64_t off = (int64_t)b * p.out_sb + (int64_t)oy * p.out_sy + (int64_t)ox * p.out_sx;
+      const float nz = (p.noise && in_img) ? nw * p.noise[((int64_t)b * p.Ho + oy) * p.Wo + ox] : 0.f;
+      const int as = lt & 1;
+      mbar_wait(t_full(as), (lt >> 1) & 1, 8);
+      tc_fence_after();
+      const int nchunks = p.block_n / 32;
+      for (int j = 0; j < nchunks; ++j, ++chunk) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + j * 32), v);
+        if (j == nchunks - 1) {
+          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty(as));
+        }
+        const int nb = n0 + j * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = v[i];
+          if (p.noise) x += nz;
+          if (p.bias) x += __ldg(p.bias + nb + i);
+          if (p.act == VT_ACT_LRELU) x = vt_lrelu(x, p.slope) * p.gain;
+          else if (p.act == VT_ACT_RELU_TANH) x = tanhf(fmaxf(x, 0.f));
+          v[i] = x;
+        }
+        if (p.res) {
+          if (in_img) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res + off + nb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 rv = __ldg(rp + i);
+              v[4 * i + 0] = v[4 * i + 0] * p.alpha + p.beta * rv.x;
+              v[4 * i + 1] = v[4 * i + 1] * p.alpha + p.beta * rv.y;
+              v[4 * i + 2] = v[4 * i + 2] * p.alpha + p.beta * rv.z;
+              v[4 * i + 3] = v[4 * i + 3] * p.alpha + p.beta * rv.w;
+            }
+          }
+        } else if (p.alpha != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+        }
+        if (p.round_tf32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = vt_round_tf32(v[i]);
+        }
+        const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
+        if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
+        named_bar_sync(1, 128);
+        const uint32_t row = sbuf + (uint32_t)r * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t dst = row + (uint32_t)((c ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                       "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_thread) {
+          tma_store_4d(&p.out_map, sbuf, nb, ox0, oy0, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (store_thread) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)f;
+  });
+  return fn;
+}
+
+// 4-D fp32 tensor map, SWIZZLE_128B, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..3.
+int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3], const uint32_t box[4],
+              const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  VT_CHECK(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_b[0], strides_b[1], strides_b[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) VT_CHECK(gd[i] >= 1 && bx[i] >= 1 && bx[i] <= 256, "conv_tc: bad %s map dim %d (dim=%llu box=%u)", what, i, (unsigned long long)gd[i], bx[i]);
+  for (int i = 0; i < 3; ++i) VT_CHECK(gs[i] % 16 == 0 && gs[i] > 0, "conv_tc: %s map stride %d (%llu B) not a positive multiple of 16", what, i, (unsigned long long)gs[i]);
+  VT_CHECK(((uintptr_t)base & 15) == 0, "conv_tc: %s base pointer not 16-byte aligned", what);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VT_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+int g_tc_mode = 1;  // 0: one TMA box per tap; 1: halo box + shifted descriptors; 2: halo + base_offset field
+
+int check_supported(const vt_conv_desc* d, bool set_err) {
+#define VT_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)
+  VT_SUP(d->Cout % 32 == 0, "conv_tc: Cout must be a multiple of 32 (got %d)", d->Cout);
+  for (int s = 0; s < d->n_src; ++s) {
+    VT_SUP(d->src_c[s] % KCH == 0, "conv_tc: src_c[%d]=%d must be a multiple of 32", s, d->src_c[s]);
+    VT_SUP(d->src_cstride[s] % 4 == 0, "conv_tc: channel stride must be a multiple of 4");
+  }
+  VT_SUP(d->stride == 1 || d->stride == 2, "conv_tc: stride must be 1 or 2");
+  VT_SUP(d->out_sx % 4 == 0 && d->out_sy % 4 == 0 && d->out_sb % 4 == 0, "conv_tc: output strides must be multiples of 4 floats");
+  VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
+  VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
+  VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
+  return 1;
+#undef VT_SUP
+}
+
+}  // namespace
+
+extern "C" int vt_set_option(const char* key, int value) {
+  if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
+  return -1;
+}
+
+extern "C" int vt_conv2d_tc_supported(const vt_conv_desc* d) {
+  if (!d || d->struct_size != (int)sizeof(vt_conv_desc)) return 0;
+  return check_supported(d, false);
+}
+
+extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
+  if (vt_validate_conv_desc(d, "conv2d_tc")) return 1;
+  if (!check_supported(d, true)) return 1;
+
+  static thread_local TcArgs a;  // large (tensor maps); reused to avoid stack churn
+  memset(&a, 0, sizeof(a));
+  // ---- output tile / N tile
+  int bn = 256;
+  while (bn > 32 && (d->Cout % bn) != 0) bn -= 32;
+  VT_CHECK(d->Cout % bn == 0, "conv_tc: no N tile for Cout=%d", d->Cout);
+  a.block_n = bn;
+  a.n_tiles = d->Cout / bn;
+  a.tiles_x = (int)vt_cdiv(d->Wo, TILE_W);
+  a.tiles_y = (int)vt_cdiv(d->Ho, TILE_H);
+  a.B = d->B;
+  const int64_t total = (int64_t)a.n_tiles * a.B * a.tiles_x * a.tiles_y;
+  VT_CHECK(total < (1LL << 31), "conv_tc: too many tiles");
+  a.total_tiles = (int)total;
+  int tc = 32;
+  while (tc < 2 * bn) tc *= 2;
+  a.tmem_cols = tc;
+  a.Ho = d->Ho; a.Wo = d->Wo; a.Cout = d->Cout; a.wB = d->wB;
+  a.bias = d->bias; a.noise = d->noise; a.noise_w = d->noise_w; a.res = d->res;
+  a.out_sb = d->out_sb; a.out_sy = d->out_sy; a.out_sx = d->out_sx;
+  a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
+
+  // ---- K iteration space
+  a.n_src = d->n_src;
+  int coff = 0;
+  for (int s = 0; s < d->n_src; ++s) { a.kchunks[s] = d->src_c[s] / KCH; a.coff[s] = coff; coff += d->src_c[s]; }
+  a.taps = d->taps;
+  int dxmin = 1 << 30, dxmax = -(1 << 30), dymin = 1 << 30, dymax = -(1 << 30);
+  for (int t = 0; t < d->taps; ++t) {
+    a.tap_w[t] = d->tap_w[t];
+    if (d->stride == 1) {
+      a.tap_view[t] = 0; a.tap_vx[t] = d->tap_dx[t]; a.tap_vy[t] = d->tap_dy[t];
+    } else {
+      const int px = d->tap_dx[t] & 1, py = d->tap_dy[t] & 1;
+      a.tap_view[t] = py * 2 + px;
+      a.tap_vx[t] = (d->tap_dx[t] - px) / 2;
+      a.tap_vy[t] = (d->tap_dy[t] - py) / 2;
+    }
+    dxmin = a.tap_vx[t] < dxmin ? a.tap_vx[t] : dxmin; dxmax = a.tap_vx[t] > dxmax ? a.tap_vx[t] : dxmax;
+    dymin = a.tap_vy[t] < dymin ? a.tap_vy[t] : dymin; dymax = a.tap_vy[t] > dymax ? a.tap_vy[t] : dymax;
+  }
+  // ---- operand staging plan
+  const int halo_w = TILE_W + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
+  const int halo_bytes = halo_w * halo_h * 128;
+  a.halo = (g_tc_mode != 0) && d->stride == 1 && d->taps > 1 && halo_w <= 256 && halo_h <= 256 &&
+           halo_bytes <= d->taps * TILE_M * 128 / 2 && halo_bytes <= 64 * 1024;
+  a.base_offset_mode = (g_tc_mode == 2);
+  a.halo_x0 = dxmin; a.halo_y0 = dymin; a.halo_w = halo_w;
+  a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
+  a.a_stage_bytes = (int)(vt_cdiv(a.a_tx_bytes, 1024) * 1024);
+  a.b_stage_bytes = bn * 128;
+  const int fixed = 2 * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  a.a_stages = a.halo ? 2 : 4;
+  a.b_stages = 4;
+  while (a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed > MAX_SMEM) {
+    if (a.b_stages > 2 && a.b_stages * a.b_stage_bytes >= a.a_stages * a.a_stage_bytes) --a.b_stages;
+    else if (a.a_stages > 2) --a.a_stages;
+    else if (a.b_stages > 2) --a.b_stages;
+    else break;
+  }
+  if (a.halo && a.a_stages < 3 && (a.a_stages + 1) * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed <= MAX_SMEM) ++a.a_stages;
+  while (a.b_stages < 8 && a.a_stages * a.a_stage_bytes + (a.b_stages + 1) * a.b_stage_bytes + fixed <= MAX_SMEM &&
+         a.b_stages < 6)
+    ++a.b_stages;
+  const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed;
+  VT_CHECK(smem_bytes <= MAX_SMEM && a.a_stages >= 2 && a.b_stages >= 2 && a.a_stages <= 8 && a.b_stages <= 8,
+           "conv_tc: shared memory plan does not fit (%d B)", smem_bytes);
+
+  // ---- tensor maps
+  for (int s = 0; s < d->n_src; ++s) {
+    const uint64_t cs = (uint64_t)d->src_cstride[s];
+    if (d->stride == 1) {
+      const uint64_t dims[4] = {cs, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+      const uint64_t str[3] = {cs * 4, (uint64_t)d->W * cs * 4, (uint64_t)d->H * d->W * cs * 4};
+      const uint32_t box[4] = {KCH, (uint32_t)(a.halo ? halo_w : TILE_W), (uint32_t)(a.halo ? halo_h : TILE_H), 1};
+      if (make_map4(&a.in_map[s][0], d->src[s], dims, str, box, "input")) return 1;
+      for (int v = 1; v < 4; ++v) a.in_map[s][v] = a.in_map[s][0];
+    } else {
+      // parity views: view (py,px)[vy][vx] = in[2*vy+py][2*vx+px]
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int vw = (d->W - px + 1) / 2, vh = (d->H - py + 1) / 2;
+          CUtensorMap* mp = &a.in_map[s][py * 2 + px];
+          if (vw < 1 || vh < 1) { *mp = a.in_map[s][0]; continue; }
+          const uint64_t dims[4] = {cs, (uint64_t)vw, (uint64_t)vh, (uint64_t)d->B};
+          const uint64_t str[3] = {2 * cs * 4, 2 * (uint64_t)d->W * cs * 4, (uint64_t)d->H * d->W * cs * 4};
+          const uint32_t box[4] = {KCH, TILE_W, TILE_H, 1};
+          if (make_map4(mp, d->src[s] + ((int64_t)py * d->W + px) * cs, dims, str, box, "input(parity)")) return 1;
+        }
+    }
+  }
+  {
+    const uint64_t wc = (uint64_t)d->w_cstride;
+    const uint64_t dims[4] = {wc, (uint64_t)d->Cout, (uint64_t)d->w_taps, (uint64_t)d->wB};
+    const uint64_t str[3] = {wc * 4, (uint64_t)d->Cout * wc * 4, (uint64_t)d->w_taps * d->Cout * wc * 4};
+    const uint32_t box[4] = {KCH, (uint32_t)bn, 1, 1};
+    if (make_map4(&a.w_map, d->weight, dims, str, box, "weight")) return 1;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    const uint64_t str[3] = {(uint64_t)d->out_sx * 4, (uint64_t)d->out_sy * 4, (uint64_t)(d->B > 1 ? d->out_sb : d->out_sy * d->Ho) * 4};
+    const uint32_t box[4] = {32, TILE_W, TILE_H, 1};
+    if (make_map4(&a.out_map, d->out, dims, str, box, "output")) return 1;
+  }
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+  });
+  VT_CHECK(attr_err == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  int grid = vt_num_sms();
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  conv_tc_kernel<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(a);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_selftest_tc_gemm(const float*, const float*, float*, int, int, int, int, void*) {
+  return vt_set_error("selftest_tc_gemm: use vt_conv2d_tc_tf32 with a 1x1 tap (tests/test_conv_tc.py)");
+}

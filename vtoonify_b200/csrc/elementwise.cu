@@ -1,0 +1,208 @@
+// elementwise.cu — HBM-bound streaming kernels: fused bias+leaky-relu, layout transforms, axpby, frame transforms.
+//
+//   fused_bias_act : y = lrelu(x + b[c], slope) * scale, written from the spec
+//                    model/stylegan/op_cpu/fused_act.py:23-34 (== op/fused_bias_act_kernel.cu case act*10+grad == 30).
+//                    float4 vectorised; the channel index is computed once per vector (no per-element div/mod).
+//   nchw<->nhwc    : 32x32 smem-tiled transposes between the API layout (NCHW) and the internal NHWC layout.
+//   frame u8<->f32 : ToTensor+Normalize(0.5,0.5) and util.tensor2cv2 (style_transfer.py:57-60, util.py:190-192).
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+fused_bias_act_vec4_kernel(const float4* __restrict__ in, const float* __restrict__ bias, float4* __restrict__ out,
+                           int64_t n4, int64_t step_b4, int size_b, float slope, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldcs(in + i);
+    float b = 0.f;
+    if (bias) b = __ldg(bias + (int)((i / step_b4) % size_b));
+    v.x = vt_lrelu(v.x + b, slope) * scale;
+    v.y = vt_lrelu(v.y + b, slope) * scale;
+    v.z = vt_lrelu(v.z + b, slope) * scale;
+    v.w = vt_lrelu(v.w + b, slope) * scale;
+    __stcs(out + i, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fused_bias_act_scalar_kernel(const float* __restrict__ in, const float* __restrict__ bias, float* __restrict__ out,
+                             int64_t n, int64_t step_b, int size_b, float slope, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float b = bias ? __ldg(bias + (int)((i / step_b) % size_b)) : 0.f;
+    out[i] = vt_lrelu(in[i] + b, slope) * scale;
+  }
+}
+
+// in: [B, C, HW] -> out: [B, HW, c_pad]; tile 32 (c) x 32 (hw)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int64_t HW, int c_pad, int round_tf32) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t hw0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* ip = in + (int64_t)b * C * HW;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t hw = hw0 + tx;
+    tile[j][tx] = (c < C && hw < HW) ? ip[(int64_t)c * HW + hw] : 0.f;
+  }
+  __syncthreads();
+  float* op = out + (int64_t)b * HW * c_pad;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t hw = hw0 + j;
+    const int c = c0 + tx;
+    if (hw < HW && c < c_pad) {
+      float v = tile[tx][j];
+      op[hw * c_pad + c] = round_tf32 ? vt_round_tf32(v) : v;
+    }
+  }
+}
+
+// in: [B, HW, c_stride] -> out: [B, C, HW]
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int64_t HW, int c_stride) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t hw0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* ip = in + (int64_t)b * HW * c_stride;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t hw = hw0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (hw < HW && c < C) ? ip[hw * c_stride + c] : 0.f;
+  }
+  __syncthreads();
+  float* op = out + (int64_t)b * C * HW;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t hw = hw0 + tx;
+    if (c < C && hw < HW) op[(int64_t)c * HW + hw] = tile[tx][j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n,
+             float sa, float sb, int round_tf32) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = a[i] * sa;
+    if (b) v += b[i] * sb;
+    out[i] = round_tf32 ? vt_round_tf32(v) : v;
+  }
+}
+
+// u8 HWC -> f32 NCHW, one thread per pixel
+__global__ void __launch_bounds__(256)
+frame_u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t HW, int swap_rb,
+                       int64_t out_batch_stride) {
+  const int b = blockIdx.y;
+  const uint8_t* ip = in + (int64_t)b * HW * 3;
+  float* op = out + (int64_t)b * out_batch_stride;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t c0 = ip[p * 3 + 0], c1 = ip[p * 3 + 1], c2 = ip[p * 3 + 2];
+    if (swap_rb) { uint8_t t = c0; c0 = c2; c2 = t; }
+    // ToTensor: v/255 ; Normalize(0.5, 0.5): (v - 0.5) / 0.5   (same op order as torchvision)
+    op[p] = (((float)c0 / 255.f) - 0.5f) / 0.5f;
+    op[HW + p] = (((float)c1 / 255.f) - 0.5f) / 0.5f;
+    op[2 * HW + p] = (((float)c2 / 255.f) - 0.5f) / 0.5f;
+  }
+}
+
+// f32 NCHW (3ch) -> clamp -> u8 HWC ; tensor2cv2: ((x + 1) * 127.5).astype(uint8) (truncation), optional RGB->BGR
+__global__ void __launch_bounds__(256)
+f32_to_frame_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t HW, int swap_rb) {
+  const int b = blockIdx.y;
+  const float* ip = in + (int64_t)b * 3 * HW;
+  uint8_t* op = out + (int64_t)b * HW * 3;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = fminf(fmaxf(ip[(int64_t)c * HW + p], -1.f), 1.f);
+      v[c] = (x + 1.0f) * 127.5f;
+    }
+    uint8_t r = (uint8_t)(int)v[0], g = (uint8_t)(int)v[1], bl = (uint8_t)(int)v[2];
+    if (swap_rb) { uint8_t t = r; r = bl; bl = t; }
+    op[p * 3 + 0] = r; op[p * 3 + 1] = g; op[p * 3 + 2] = bl;
+  }
+}
+
+inline unsigned grid_for(int64_t work_items, int threads) {
+  int64_t blocks = vt_cdiv(work_items, threads);
+  const int64_t cap = (int64_t)vt_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace
+
+extern "C" int vt_fused_bias_act_f32(const float* in, const float* bias, float* out, int64_t n, int64_t step_b,
+                                     int size_b, float negative_slope, float scale, void* stream) {
+  VT_CHECK(in && out, "fused_bias_act: null pointer");
+  VT_CHECK(n >= 0, "fused_bias_act: negative size");
+  if (n == 0) return 0;
+  if (bias) VT_CHECK(step_b >= 1 && size_b >= 1, "fused_bias_act: bad bias broadcast (step_b=%lld size_b=%d)", (long long)step_b, size_b);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (n % 4 == 0) && (!bias || step_b % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  if (vec) {
+    fused_bias_act_vec4_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>((const float4*)in, bias, (float4*)out, n / 4,
+                                                                    bias ? step_b / 4 : 1, bias ? size_b : 1,
+                                                                    negative_slope, scale);
+  } else {
+    fused_bias_act_scalar_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, bias, out, n, bias ? step_b : 1,
+                                                                  bias ? size_b : 1, negative_slope, scale);
+  }
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, int c_pad, int round_tf32, void* stream) {
+  VT_CHECK(in && out && B >= 1 && C >= 1 && H >= 1 && W >= 1 && c_pad >= C, "nchw_to_nhwc: bad args");
+  const int64_t HW = (int64_t)H * W;
+  VT_CHECK(B <= 65535 && vt_cdiv(c_pad, 32) <= 65535, "nchw_to_nhwc: grid too large");
+  dim3 grid((unsigned)vt_cdiv(HW, 32), (unsigned)vt_cdiv(c_pad, 32), (unsigned)B);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW, c_pad, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, int c_stride, void* stream) {
+  VT_CHECK(in && out && B >= 1 && C >= 1 && H >= 1 && W >= 1 && c_stride >= C, "nhwc_to_nchw: bad args");
+  const int64_t HW = (int64_t)H * W;
+  VT_CHECK(B <= 65535 && vt_cdiv(C, 32) <= 65535, "nhwc_to_nchw: grid too large");
+  dim3 grid((unsigned)vt_cdiv(HW, 32), (unsigned)vt_cdiv(C, 32), (unsigned)B);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW, c_stride);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_axpby_f32(const float* a, const float* b, float* out, int64_t n, float scale_a, float scale_b,
+                            int round_tf32, void* stream) {
+  VT_CHECK(a && out && n >= 0, "axpby: bad args");
+  if (n == 0) return 0;
+  axpby_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, scale_a, scale_b, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_frame_u8_to_f32(const uint8_t* in, float* out, int B, int H, int W, int swap_rb,
+                                  int64_t out_batch_stride, void* stream) {
+  VT_CHECK(in && out && B >= 1 && B <= 65535 && H >= 1 && W >= 1, "frame_u8_to_f32: bad args");
+  const int64_t HW = (int64_t)H * W;
+  VT_CHECK(out_batch_stride >= 3 * HW, "frame_u8_to_f32: out_batch_stride too small");
+  dim3 grid(grid_for(HW, 256), (unsigned)B);
+  frame_u8_to_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, HW, swap_rb, out_batch_stride);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_f32_to_frame_u8(const float* in, uint8_t* out, int B, int H, int W, int swap_rb, void* stream) {
+  VT_CHECK(in && out && B >= 1 && B <= 65535 && H >= 1 && W >= 1, "f32_to_frame_u8: bad args");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(grid_for(HW, 256), (unsigned)B);
+  f32_to_frame_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, HW, swap_rb);
+  VT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,132 @@
+// modulate.cu — per-style constants of the modulated convolution and the small linears.
+//
+//   vt_linear_f32           : EqualLinear.forward (model/stylegan/model.py:153-162): F.linear(x, W*scale, b*lr_mul)
+//                             [+ fused_leaky_relu].  One warp per output element, shuffle reduction.
+//   vt_modulate_weights_f32 : ModulatedConv2d fused branch (model/stylegan/model.py:259-267):
+//                             w'[b,n,c,t] = (scale*W[n,c,t]) * s[b,c];  demod[b,n] = rsqrt(sum_{c,t} w'^2 + 1e-8);
+//                             written in the conv kernels' layout [b][t][n][c_pad] (K-major rows of one tap,
+//                             128-byte multiples so a TMA box of 32 channels is one swizzle row).
+//                             With style == NULL it is the plain re-layout used for nn.Conv2d / EqualConv2d weights.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
+              float* __restrict__ out, int rows, int in_dim, int out_dim, float w_scale, float b_scale, int act) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows * out_dim) return;
+  const int r = warp / out_dim, o = warp % out_dim;
+  const float* x = in + (int64_t)r * in_dim;
+  const float* w = weight + (int64_t)o * in_dim;
+  float acc = 0.f;
+  for (int i = lane; i < in_dim; i += 32) acc += x[i] * (w[i] * w_scale);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float v = acc;
+    const float b = bias ? bias[o] * b_scale : 0.f;
+    if (act == 1) v = vt_lrelu(v + b, 0.2f) * 1.4142135623730951f;
+    else if (act == 2) v = vt_lrelu(v + b, 0.2f);
+    else v = v + b;
+    out[(int64_t)r * out_dim + o] = v;
+  }
+}
+
+// PixelNorm (model/stylegan/model.py:13-18): x * rsqrt(mean(x^2, dim=1) + 1e-8); one warp per row
+__global__ void __launch_bounds__(256)
+pixelnorm_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int dim) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* x = in + (int64_t)warp * dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) ss = fmaf(x[i], x[i], ss);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+  const float r = 1.0f / sqrtf(ss / (float)dim + 1e-8f);
+  for (int i = lane; i < dim; i += 32) out[(int64_t)warp * dim + i] = x[i] * r;
+}
+
+// grid (Cout, wB); block 256. Each block owns one (b, n) filter row of Cin*taps weights.
+__global__ void __launch_bounds__(256)
+modulate_weights_kernel(const float* __restrict__ W, const float* __restrict__ style, float* __restrict__ out,
+                        int Cout, int Cin, int taps, int cin_pad, float scale, int demodulate, int round_tf32) {
+  const int n = blockIdx.x, b = blockIdx.y;
+  const float* wrow = W + (int64_t)n * Cin * taps;
+  const float* srow = style ? style + (int64_t)b * Cin : nullptr;
+  __shared__ float red[32];
+  __shared__ float s_demod;
+  float d = 1.f;
+  if (demodulate) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < Cin * taps; i += blockDim.x) {
+      const int c = i / taps;
+      float w = scale * wrow[i];
+      if (srow) w = w * srow[c];
+      ss += w * w;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (threadIdx.x == 0) s_demod = 1.0f / sqrtf(v + 1e-8f);
+    }
+    __syncthreads();
+    d = s_demod;
+  }
+  float* obase = out + ((int64_t)b * taps * Cout + n) * cin_pad;  // + t*Cout*cin_pad + c
+  for (int i = threadIdx.x; i < cin_pad * taps; i += blockDim.x) {
+    const int t = i / cin_pad, c = i % cin_pad;
+    float v = 0.f;
+    if (c < Cin) {
+      v = scale * wrow[c * taps + t];
+      if (srow) v = v * srow[c];
+      if (demodulate) v = v * d;
+      if (round_tf32) v = vt_round_tf32(v);
+    }
+    obase[(int64_t)t * Cout * cin_pad + c] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int vt_linear_f32(const float* in, const float* weight, const float* bias, float* out, int rows, int in_dim,
+                             int out_dim, float w_scale, float b_scale, int act, void* stream) {
+  VT_CHECK(in && weight && out && rows >= 1 && in_dim >= 1 && out_dim >= 1, "linear: bad args");
+  VT_CHECK(act >= 0 && act <= 2, "linear: act must be 0, 1 or 2");
+  const int64_t warps = (int64_t)rows * out_dim;
+  const int threads = 256;
+  const int64_t blocks = vt_cdiv(warps * 32, threads);
+  VT_CHECK(blocks < (1LL << 31), "linear: too large");
+  linear_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(in, weight, bias, out, rows, in_dim, out_dim,
+                                                                       w_scale, b_scale, act);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_pixelnorm_f32(const float* in, float* out, int rows, int dim, void* stream) {
+  VT_CHECK(in && out && rows >= 1 && dim >= 1, "pixelnorm: bad args");
+  pixelnorm_kernel<<<(unsigned)vt_cdiv((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, dim);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_modulate_weights_f32(const float* W, const float* style, float* out, int wB, int Cout, int Cin,
+                                       int kh, int kw, int cin_pad, float scale, int demodulate, int round_tf32,
+                                       void* stream) {
+  VT_CHECK(W && out, "modulate_weights: null pointer");
+  VT_CHECK(wB >= 1 && Cout >= 1 && Cin >= 1 && kh >= 1 && kw >= 1 && cin_pad >= Cin, "modulate_weights: bad shape");
+  VT_CHECK(style || wB == 1, "modulate_weights: style == NULL requires wB == 1");
+  VT_CHECK(wB <= 65535, "modulate_weights: batch too large");
+  dim3 grid((unsigned)Cout, (unsigned)wB);
+  modulate_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, style, out, Cout, Cin, kh * kw, cin_pad, scale,
+                                                                 demodulate, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,233 @@
+// norm_fir.cu — instance-norm statistics, AdaIN apply, and the NHWC FIR (Blur) with fused StyledConv epilogue.
+//
+//   vt_instnorm_stats_nhwc / vt_adain_apply_nhwc : AdaptiveInstanceNorm.forward (model/dualstylegan.py:16-21):
+//        nn.InstanceNorm2d(affine=False) = (x - mean) / sqrt(biased_var + 1e-5) per (b, c) plane, then gamma*x + beta.
+//        mode 1 evaluates the virtual concat cat(f_G, |f_G - f_E|) of Fusion.forward (model/vtoonify.py:125-126)
+//        without materialising it for the statistics pass.
+//   vt_fir_nhwc_f32 : Blur.forward after the stride-2 transposed conv (model/stylegan/model.py:74-90,285) =
+//        upfirdn2d(x, k, pad=(p0,p1)) with up=down=1, on NHWC, with NoiseInjection + FusedLeakyReLU
+//        (model/stylegan/model.py:315-320,364-370) applied in the same pass. Each thread owns 4 channels (float4)
+//        of a 1 x 4 vertical strip of outputs so every input row is loaded once per strip.
+#include "common.cuh"
+
+namespace {
+
+// grid (chunks, B); dyn smem: Cs*2 floats
+__global__ void __launch_bounds__(256)
+instnorm_partial_kernel(const float* __restrict__ in, const float* __restrict__ in2, int mode, int64_t HW, int C,
+                        int c_stride, int64_t chunk, double* __restrict__ ws) {
+  extern __shared__ float sacc[];  // [Cs][2]
+  const int Cs = mode ? 2 * C : C;
+  for (int i = threadIdx.x; i < Cs * 2; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int nvec = C / 4;
+  const int64_t p_begin = (int64_t)blockIdx.x * chunk;
+  const int64_t p_end = (p_begin + chunk < HW) ? p_begin + chunk : HW;
+  const float* ip = in + (int64_t)b * HW * c_stride;
+  const float* ip2 = mode ? in2 + (int64_t)b * HW * c_stride : nullptr;
+  // each thread owns one float4 channel group `v` and every pstep-th pixel of the chunk
+  const int pstep = blockDim.x / nvec;           // >= 1 (nvec <= 256 checked by the host)
+  const int v = threadIdx.x % nvec, lane_p = threadIdx.x / nvec;
+  if (lane_p < pstep) {
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
+    for (int64_t p = p_begin + lane_p; p < p_end; p += pstep) {
+      const float4 a = *reinterpret_cast<const float4*>(ip + p * c_stride + v * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[i] += av[i]; q[i] = fmaf(av[i], av[i], q[i]); }
+      if (mode) {
+        const float4 e = *reinterpret_cast<const float4*>(ip2 + p * c_stride + v * 4);
+        const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float d = fabsf(av[i] - ev[i]); s2[i] += d; q2[i] = fmaf(d, d, q2[i]); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(&sacc[(v * 4 + i) * 2 + 0], s[i]);
+      atomicAdd(&sacc[(v * 4 + i) * 2 + 1], q[i]);
+      if (mode) {
+        atomicAdd(&sacc[(C + v * 4 + i) * 2 + 0], s2[i]);
+        atomicAdd(&sacc[(C + v * 4 + i) * 2 + 1], q2[i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cs * 2; i += blockDim.x) atomicAdd(&ws[(int64_t)b * Cs * 2 + i], (double)sacc[i]);
+}
+
+__global__ void instnorm_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int n, double inv_hw, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = ws[i * 2] * inv_hw;
+  double var = ws[i * 2 + 1] * inv_hw - mean * mean;
+  if (var < 0) var = 0;
+  stats[i * 2] = (float)mean;
+  stats[i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// one thread per (pixel, float4 of the OUTPUT channels Cs)
+__global__ void __launch_bounds__(256)
+adain_apply_kernel(const float* __restrict__ in, const float* __restrict__ in2, int mode, int64_t HW, int C, int c_stride,
+                   const float* __restrict__ stats, const float* __restrict__ gb, float* __restrict__ out, int round_tf32) {
+  const int Cs = mode ? 2 * C : C;
+  const int nvec = Cs / 4;
+  const int b = blockIdx.y;
+  const int64_t total = HW * nvec;
+  const float* st = stats + (int64_t)b * Cs * 2;
+  const float* gamma = gb + (int64_t)b * 2 * Cs;
+  const float* beta = gamma + Cs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / nvec;
+    const int c = (int)(i % nvec) * 4;
+    float x[4];
+    if (!mode || c < C) {
+      const float4 a = *reinterpret_cast<const float4*>(in + ((int64_t)b * HW + p) * c_stride + c);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(in + ((int64_t)b * HW + p) * c_stride + (c - C));
+      const float4 e = *reinterpret_cast<const float4*>(in2 + ((int64_t)b * HW + p) * c_stride + (c - C));
+      x[0] = fabsf(a.x - e.x); x[1] = fabsf(a.y - e.y); x[2] = fabsf(a.z - e.z); x[3] = fabsf(a.w - e.w);
+    }
+    float y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xn = (x[k] - st[(c + k) * 2]) * st[(c + k) * 2 + 1];
+      float v = gamma[c + k] * xn + beta[c + k];
+      y[k] = round_tf32 ? vt_round_tf32(v) : v;
+    }
+    *reinterpret_cast<float4*>(out + ((int64_t)b * HW + p) * Cs + c) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+
+constexpr int FIR_R = 4;      // output rows per thread
+constexpr int FIR_MAXK = 8;   // max kernel extent
+
+__global__ void __launch_bounds__(256)
+fir_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ kernel, float* __restrict__ out, int H, int W,
+                int C, int Ho, int Wo, int kh, int kw, int pad0, const float* __restrict__ bias,
+                const float* __restrict__ noise, const float* __restrict__ noise_w, int act, float slope, float gain,
+                int round_tf32) {
+  __shared__ float sk[FIR_MAXK * FIR_MAXK];  // flipped kernel: sk[ky][kx] multiplies in[oy+ky-pad0][ox+kx-pad0]
+  if (threadIdx.x < kh * kw) {
+    const int ky = threadIdx.x / kw, kx = threadIdx.x % kw;
+    sk[threadIdx.x] = kernel[(kh - 1 - ky) * kw + (kw - 1 - kx)];
+  }
+  __syncthreads();
+  const int nvec = C / 4;
+  const int b = blockIdx.z;
+  const int strips = (Ho + FIR_R - 1) / FIR_R;
+  const int64_t total = (int64_t)strips * Wo * nvec;
+  const float nw = noise ? *noise_w : 0.f;
+  const float* ip = in + (int64_t)b * H * W * C;
+  float* op = out + (int64_t)b * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int64_t r = i / nvec;
+    const int ox = (int)(r % Wo);
+    const int oy0 = (int)(r / Wo) * FIR_R;
+    float4 acc[FIR_R];
+#pragma unroll
+    for (int j = 0; j < FIR_R; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // input rows oy0 - pad0 .. oy0 + FIR_R - 1 + kh - 1 - pad0
+    for (int ry = 0; ry < FIR_R + kh - 1; ++ry) {
+      const int iy = oy0 - pad0 + ry;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ix = ox - pad0 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float4 a = *reinterpret_cast<const float4*>(ip + ((int64_t)iy * W + ix) * C + v * 4);
+#pragma unroll
+        for (int j = 0; j < FIR_R; ++j) {
+          const int ky = ry - j;
+          if (ky >= 0 && ky < kh) {
+            const float w = sk[ky * kw + kx];
+            acc[j].x = fmaf(a.x, w, acc[j].x); acc[j].y = fmaf(a.y, w, acc[j].y);
+            acc[j].z = fmaf(a.z, w, acc[j].z); acc[j].w = fmaf(a.w, w, acc[j].w);
+          }
+        }
+      }
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = *reinterpret_cast<const float4*>(bias + v * 4);
+#pragma unroll
+    for (int j = 0; j < FIR_R; ++j) {
+      const int oy = oy0 + j;
+      if (oy >= Ho) break;
+      float o[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float nz = noise ? nw * noise[((int64_t)b * Ho + oy) * Wo + ox] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t = o[k];
+        if (noise) t += nz;
+        if (act) t = vt_lrelu(t + bb[k], slope) * gain;
+        else if (bias) t += bb[k];
+        o[k] = round_tf32 ? vt_round_tf32(t) : t;
+      }
+      *reinterpret_cast<float4*>(op + ((int64_t)oy * Wo + ox) * C + v * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
+                                      float eps, float* stats, double* ws, void* stream) {
+  VT_CHECK(in && stats && ws && (mode == 0 || (mode == 1 && in2)), "instnorm_stats: bad pointers/mode");
+  VT_CHECK(B >= 1 && B <= 65535 && HW >= 1 && C >= 4 && C % 4 == 0 && c_stride >= C && c_stride % 4 == 0, "instnorm_stats: bad shape");
+  VT_CHECK(C / 4 <= 256, "instnorm_stats: C must be <= 1024");
+  const int Cs = mode ? 2 * C : C;
+  cudaStream_t st = (cudaStream_t)stream;
+  VT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)B * Cs * 2, st));
+  const int nvec = C / 4;
+  const int plan = 256 / nvec;                      // pixels processed concurrently by a block
+  int64_t chunk = (int64_t)plan * 128;              // ~128 pixels per thread
+  if (chunk < 256) chunk = 256;
+  int64_t chunks = vt_cdiv(HW, chunk);
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  instnorm_partial_kernel<<<grid, 256, (size_t)Cs * 2 * sizeof(float), st>>>(in, in2, mode, HW, C, c_stride, chunk, ws);
+  VT_LAUNCH_CHECK();
+  const int n = B * Cs;
+  instnorm_finalize_kernel<<<(unsigned)vt_cdiv(n, 256), 256, 0, st>>>(ws, stats, n, 1.0 / (double)HW, eps);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_adain_apply_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
+                                   const float* stats, const float* gamma_beta, float* out, int round_tf32, void* stream) {
+  VT_CHECK(in && stats && gamma_beta && out && (mode == 0 || (mode == 1 && in2)), "adain_apply: bad pointers/mode");
+  VT_CHECK(B >= 1 && B <= 65535 && HW >= 1 && C >= 4 && C % 4 == 0 && c_stride >= C && c_stride % 4 == 0, "adain_apply: bad shape");
+  const int Cs = mode ? 2 * C : C;
+  const int64_t total = HW * (Cs / 4);
+  int64_t blocks = vt_cdiv(total, 256);
+  const int64_t cap = (int64_t)vt_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)B);
+  adain_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in2, mode, HW, C, c_stride, stats, gamma_beta, out, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_fir_nhwc_f32(const float* in, const float* kernel, float* out, int B, int H, int W, int C, int kh, int kw,
+                               int pad0, int pad1, const float* bias, const float* noise, const float* noise_w, int act,
+                               float slope, float gain, int round_tf32, void* stream) {
+  VT_CHECK(in && kernel && out, "fir_nhwc: null pointer");
+  VT_CHECK(B >= 1 && B <= 65535 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0, "fir_nhwc: bad shape (C must be a multiple of 4)");
+  VT_CHECK(kh >= 1 && kw >= 1 && kh <= FIR_MAXK && kw <= FIR_MAXK, "fir_nhwc: kernel extent must be <= %d", FIR_MAXK);
+  VT_CHECK(pad0 >= 0 && pad1 >= 0, "fir_nhwc: negative pad not supported on the NHWC path");
+  VT_CHECK(!noise || noise_w, "fir_nhwc: noise without noise_w");
+  const int Ho = H + pad0 + pad1 - kh + 1, Wo = W + pad0 + pad1 - kw + 1;
+  VT_CHECK(Ho >= 1 && Wo >= 1, "fir_nhwc: empty output");
+  const int strips = (Ho + FIR_R - 1) / FIR_R;
+  const int64_t total = (int64_t)strips * Wo * (C / 4);
+  int64_t blocks = vt_cdiv(total, 256);
+  const int64_t cap = (int64_t)vt_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, 1, (unsigned)B);
+  fir_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, kernel, out, H, W, C, Ho, Wo, kh, kw, pad0, bias, noise,
+                                                         noise_w, act, slope, gain, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,389 @@
+"""Functional layer over the C-ABI: every function launches hand-written sm_100a kernels from
+libvtoonify_b200.so on torch CUDA tensors (torch is used for memory and streams only).
+
+Internal activation layout is NHWC (``[B, H, W, C]`` contiguous fp32); the reference-facing modules
+convert at the API boundary (NCHW in / out, or zero-copy when a tensor is channels_last).
+"""
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU_TANH, ConvDesc, SmallNDesc, check
+
+SQRT2 = math.sqrt(2.0)
+
+# "tf32": tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate) — the product path.
+# "fp32": every convolution on the fp32-exact FFMA kernel (used to cross-check the tensor-core path).
+_precision = "tf32"
+
+
+def set_precision(p: str) -> str:
+    global _precision
+    if p not in ("tf32", "fp32"):
+        raise ValueError("precision must be 'tf32' or 'fp32'")
+    old, _precision = _precision, p
+    return old
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def _round_flag() -> int:
+    return 1 if _precision == "tf32" else 0
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.VtError("vtoonify_b200 ops need CUDA tensors: there is no CPU fallback "
+                               "(use the reference's op_cpu or oracle/ for CPU)")
+        if t.dtype != torch.float32:
+            raise _lib.VtError(f"vtoonify_b200 ops are fp32 I/O (got {t.dtype})")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------------------------
+def is_channels_last_view(x: torch.Tensor) -> bool:
+    """True if logical-NCHW ``x`` is physically NHWC-contiguous."""
+    if x.dim() != 4:
+        return False
+    B, C, H, W = x.shape
+    return x.stride() == (H * W * C, 1, W * C, C) or (B == 1 and x.stride()[1:] == (1, W * C, C))
+
+
+def to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None, round_tf32: Optional[bool] = None) -> torch.Tensor:
+    """NCHW (any strides) -> NHWC ``[B,H,W,c_pad]`` with zero-filled pad channels."""
+    _req_cuda(x)
+    B, C, H, W = x.shape
+    c_pad = C if c_pad is None else c_pad
+    if c_pad == C and is_channels_last_view(x):
+        return x.permute(0, 2, 3, 1)
+    x = x.contiguous()
+    out = torch.empty((B, H, W, c_pad), device=x.device, dtype=torch.float32)
+    rt = _round_flag() if round_tf32 is None else int(round_tf32)
+    check(_lib.load().vt_nchw_to_nhwc_f32(x.data_ptr(), out.data_ptr(), B, C, H, W, c_pad, rt, _stream()))
+    return out
+
+
+def to_nchw(x: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
+    """NHWC ``[B,H,W,Cs]`` -> contiguous NCHW ``[B,C,H,W]`` (first C channels)."""
+    _req_cuda(x)
+    B, H, W, Cs = x.shape
+    C = Cs if C is None else C
+    out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_nhwc_to_nchw_f32(x.data_ptr(), out.data_ptr(), B, C, H, W, Cs, _stream()))
+    return out
+
+
+def nhwc_as_nchw_view(x: torch.Tensor) -> torch.Tensor:
+    """Zero-copy: NHWC tensor seen as a logical NCHW (channels_last) tensor."""
+    return x.permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# a1 / a2: the reference's two custom ops (planar NCHW API)
+# ----------------------------------------------------------------------------------------------
+def upfirdn2d_planar(x: torch.Tensor, kernel: torch.Tensor, up: Tuple[int, int], down: Tuple[int, int],
+                     pad: Tuple[int, int, int, int]) -> torch.Tensor:
+    _req_cuda(x, kernel)
+    B, C, H, W = x.shape
+    kh, kw = kernel.shape
+    lib = _lib.load()
+    oh, ow = _lib.c_int(), _lib.c_int()
+    check(lib.vt_upfirdn2d_out_size(H, W, kh, kw, up[0], up[1], down[0], down[1], pad[0], pad[1], pad[2], pad[3], oh, ow))
+    if oh.value < 1 or ow.value < 1:
+        raise _lib.VtError(f"upfirdn2d: empty output {oh.value}x{ow.value}")
+    x = x.contiguous()
+    kernel = kernel.contiguous()
+    out = torch.empty((B, C, oh.value, ow.value), device=x.device, dtype=torch.float32)
+    check(lib.vt_upfirdn2d_f32(x.data_ptr(), kernel.data_ptr(), out.data_ptr(), B * C, H, W, kh, kw, up[0], up[1],
+                               down[0], down[1], pad[0], pad[1], pad[2], pad[3], _stream()))
+    return out
+
+
+def fused_bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], negative_slope: float, scale: float) -> torch.Tensor:
+    _req_cuda(x, bias)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    n = x.numel()
+    if bias is not None:
+        if x.dim() < 2 or bias.dim() != 1 or bias.shape[0] != x.shape[1]:
+            raise _lib.VtError(f"fused_leaky_relu: bias {tuple(bias.shape)} does not match dim 1 of {tuple(x.shape)}")
+        step_b = 1
+        for s in x.shape[2:]:
+            step_b *= s
+        bias = bias.contiguous()
+        check(_lib.load().vt_fused_bias_act_f32(x.data_ptr(), bias.data_ptr(), out.data_ptr(), n, step_b, x.shape[1],
+                                                negative_slope, scale, _stream()))
+    else:
+        check(_lib.load().vt_fused_bias_act_f32(x.data_ptr(), None, out.data_ptr(), n, 1, 1, negative_slope, scale, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# small dense layers
+# ----------------------------------------------------------------------------------------------
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], w_scale: float = 1.0,
+           b_scale: float = 1.0, act: int = 0) -> torch.Tensor:
+    """``act``: 0 none, 1 fused_leaky_relu (0.2, *sqrt2), 2 LeakyReLU(0.2)."""
+    _req_cuda(x, weight, bias)
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1]).contiguous()
+    out = torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_linear_f32(x2.data_ptr(), weight.contiguous().data_ptr(), _ptr(None if bias is None else bias.contiguous()),
+                                    out.data_ptr(), x2.shape[0], x2.shape[1], weight.shape[0], w_scale, b_scale, act, _stream()))
+    return out.reshape(*shp[:-1], weight.shape[0])
+
+
+def pixelnorm(x: torch.Tensor) -> torch.Tensor:
+    _req_cuda(x)
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    out = torch.empty_like(x2)
+    check(_lib.load().vt_pixelnorm_f32(x2.data_ptr(), out.data_ptr(), x2.shape[0], x2.shape[1], _stream()))
+    return out.reshape(x.shape)
+
+
+# ----------------------------------------------------------------------------------------------
+# a3: weights
+# ----------------------------------------------------------------------------------------------
+def _pad32(c: int) -> int:
+    return (c + 31) // 32 * 32
+
+
+def prep_weights(W: torch.Tensor, style: Optional[torch.Tensor] = None, scale: float = 1.0, demodulate: bool = False,
+                 cin_pad: Optional[int] = None) -> torch.Tensor:
+    """``W`` [Cout,Cin,kh,kw] (+ optional per-sample ``style`` [B,Cin]) -> conv-kernel layout
+    ``[wB, kh*kw, Cout, cin_pad]`` = (scale*W)*style*demod (model/stylegan/model.py:259-267)."""
+    _req_cuda(W, style)
+    Cout, Cin, kh, kw = W.shape
+    cin_pad = _pad32(Cin) if cin_pad is None else cin_pad
+    wB = 1 if style is None else style.shape[0]
+    out = torch.empty((wB, kh * kw, Cout, cin_pad), device=W.device, dtype=torch.float32)
+    check(_lib.load().vt_modulate_weights_f32(W.contiguous().data_ptr(), _ptr(None if style is None else style.contiguous()),
+                                              out.data_ptr(), wB, Cout, Cin, kh, kw, cin_pad, float(scale),
+                                              int(demodulate), _round_flag(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------------
+def conv_taps(k: int, padding: int, dilation: int = 1):
+    """(dy, dx, weight-slab) of a k x k cross-correlation with zero padding."""
+    return [(ky * dilation - padding, kx * dilation - padding, ky * k + kx) for ky in range(k) for kx in range(k)]
+
+
+def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride: int, Ho: int, Wo: int,
+                out: Optional[torch.Tensor] = None, out_view: Optional[Tuple[int, int, int, int]] = None,
+                src_c: Optional[Sequence[int]] = None,
+                bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                noise_w: Optional[torch.Tensor] = None, act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0,
+                res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
+                precision: Optional[str] = None) -> torch.Tensor:
+    """General NHWC convolution (virtual channel-concat of ``srcs``).
+
+    ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
+    ``out_view``: (offset_elems, sb, sy, sx) strided view into ``out`` (used for polyphase transposed conv).
+    """
+    prec = precision or _precision
+    B, H, W, _ = srcs[0].shape
+    wB, w_taps, Cout, w_cs = weight.shape
+    _req_cuda(weight, bias, noise, noise_w, res, *srcs)
+    d = ConvDesc()
+    d.struct_size = _lib.ctypes.sizeof(ConvDesc)
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        if not s.is_contiguous() or s.shape[:3] != (B, H, W):
+            raise _lib.VtError("conv2d_nhwc: sources must be contiguous NHWC with equal B,H,W")
+        d.src[i] = s.data_ptr()
+        d.src_c[i] = s.shape[3] if src_c is None else src_c[i]
+        d.src_cstride[i] = s.shape[3]
+    d.B, d.H, d.W, d.Ho, d.Wo = B, H, W, Ho, Wo
+    d.stride = stride
+    d.taps = len(taps)
+    for t, (dy, dx, tw) in enumerate(taps):
+        d.tap_dy[t], d.tap_dx[t], d.tap_w[t] = dy, dx, tw
+    d.weight = weight.data_ptr()
+    d.wB, d.w_taps, d.w_cstride, d.Cout = wB, w_taps, w_cs, Cout
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), device=srcs[0].device, dtype=torch.float32)
+    if out_view is None:
+        off, sb, sy, sx = 0, Ho * Wo * Cout, Wo * Cout, Cout
+        if out.shape != (B, Ho, Wo, Cout) or not out.is_contiguous():
+            raise _lib.VtError("conv2d_nhwc: bad out tensor")
+    else:
+        off, sb, sy, sx = out_view
+    d.out = out.data_ptr() + 4 * off
+    d.out_sb, d.out_sy, d.out_sx = sb, sy, sx
+    d.bias = _ptr(bias)
+    d.noise = _ptr(noise)
+    d.noise_w = _ptr(noise_w)
+    d.act, d.slope, d.gain = act, slope, gain
+    if res is not None:
+        if out_view is not None or res.shape != (B, Ho, Wo, Cout) or not res.is_contiguous():
+            raise _lib.VtError("conv2d_nhwc: residual must match a dense output")
+        d.res = res.data_ptr()
+    d.alpha, d.beta = alpha, beta
+    d.round_tf32 = _round_flag()
+    lib = _lib.load()
+    if prec == "tf32" and lib.vt_conv2d_tc_supported(d):
+        check(lib.vt_conv2d_tc_tf32(d, _stream()))
+    else:
+        check(lib.vt_conv2d_direct_f32(d, _stream()))
+    return out
+
+
+def conv_out_size(n: int, k: int, stride: int, padding: int, dilation: int) -> int:
+    return (n + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+
+
+def conv_transpose2d_s2_k3_nhwc(x: torch.Tensor, weight: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+    """F.conv_transpose2d(x, w, stride=2, padding=0) with a 3x3 kernel as 4 polyphase convolutions
+    (model/stylegan/model.py:273-283).  ``weight`` in prep layout with slab index ky*3+kx of the (un-flipped)
+    W[cout, cin, ky, kx].  out[2i+ky, 2j+kx] += x[i,j] * W[:, :, ky, kx]  ->  [B, 2H+1, 2W+1, Cout]."""
+    B, H, W, _ = x.shape
+    Cout = weight.shape[2]
+    Hf, Wf = 2 * H + 1, 2 * W + 1
+    out = torch.empty((B, Hf, Wf, Cout), device=x.device, dtype=torch.float32)
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for ky in range(py, 3, 2):
+                for kx in range(px, 3, 2):
+                    taps.append((-(ky - py) // 2, -(kx - px) // 2, ky * 3 + kx))
+            Ho = H + 1 if py == 0 else H
+            Wo = W + 1 if px == 0 else W
+            view = ((py * Wf + px) * Cout, Hf * Wf * Cout, 2 * Wf * Cout, 2 * Cout)
+            conv2d_nhwc([x], weight, taps, 1, Ho, Wo, out=out, out_view=view, precision=precision)
+    return out
+
+
+def fir_nhwc(x: torch.Tensor, kernel: torch.Tensor, pad: Tuple[int, int], bias: Optional[torch.Tensor] = None,
+             noise: Optional[torch.Tensor] = None, noise_w: Optional[torch.Tensor] = None, act: bool = False,
+             slope: float = 0.2, gain: float = SQRT2) -> torch.Tensor:
+    _req_cuda(x, kernel, bias, noise, noise_w)
+    B, H, W, C = x.shape
+    kh, kw = kernel.shape
+    Ho, Wo = H + pad[0] + pad[1] - kh + 1, W + pad[0] + pad[1] - kw + 1
+    out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_fir_nhwc_f32(x.data_ptr(), kernel.contiguous().data_ptr(), out.data_ptr(), B, H, W, C, kh, kw,
+                                      pad[0], pad[1], _ptr(bias), _ptr(noise), _ptr(noise_w), int(act), slope, gain,
+                                      _round_flag(), _stream()))
+    return out
+
+
+def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], taps, Cout: int, B: int, H: int, W: int,
+                planar: Optional[torch.Tensor] = None, planar_weight: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, skip: Optional[torch.Tensor] = None,
+                skip_kernel: Optional[torch.Tensor] = None, mul_src: Optional[torch.Tensor] = None):
+    """Cout<=4 convolution with planar NCHW output ``[B,Cout,H,W]``; optionally also returns ``mul_src * out[:,0]``."""
+    _req_cuda(src, weight, planar, planar_weight, bias, skip, skip_kernel, mul_src)
+    dev = (src if src is not None else planar).device
+    d = SmallNDesc()
+    d.struct_size = _lib.ctypes.sizeof(SmallNDesc)
+    if planar is not None:
+        planar = planar.contiguous()
+        d.n_planar = planar.shape[1]
+        d.planar = planar.data_ptr()
+        d.planar_weight = planar_weight.contiguous().data_ptr()
+    if src is not None:
+        d.src = src.data_ptr()
+        d.src_c = src.shape[3]
+        d.src_cstride = src.shape[3]
+        d.weight = weight.data_ptr()
+        d.wB, d.w_taps, _, d.w_cstride = weight.shape
+    else:
+        d.wB, d.w_taps = 1, (planar_weight.shape[0] if planar_weight is not None else 1)
+    d.Cout = Cout
+    d.B, d.H, d.W = B, H, W
+    d.taps = len(taps)
+    for t, (dy, dx, tw) in enumerate(taps):
+        d.tap_dy[t], d.tap_dx[t], d.tap_w[t] = dy, dx, tw
+    d.bias = _ptr(bias)
+    d.act = act
+    if skip is not None:
+        skip = skip.contiguous()
+        d.skip = skip.data_ptr()
+        d.skip_kernel = skip_kernel.contiguous().data_ptr()
+    out = torch.empty((B, Cout, H, W), device=dev, dtype=torch.float32)
+    d.out = out.data_ptr()
+    mul_out = None
+    if mul_src is not None:
+        mul_out = torch.empty_like(mul_src)
+        d.mul_out, d.mul_src, d.mul_c = mul_out.data_ptr(), mul_src.data_ptr(), mul_src.shape[3]
+    d.round_tf32 = _round_flag()
+    check(_lib.load().vt_smalln_conv_f32(d, _stream()))
+    return (out, mul_out) if mul_src is not None else out
+
+
+# ----------------------------------------------------------------------------------------------
+# a7: AdaIN
+# ----------------------------------------------------------------------------------------------
+def instnorm_stats(x: torch.Tensor, x2: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    """Per-(b,c) (mean, rstd) of ``x`` (or of cat(x, |x - x2|) when ``x2`` is given)."""
+    _req_cuda(x, x2)
+    B, H, W, C = x.shape
+    mode = 0 if x2 is None else 1
+    Cs = C * (2 if mode else 1)
+    stats = torch.empty((B, Cs, 2), device=x.device, dtype=torch.float32)
+    ws = torch.empty((B * Cs * 2,), device=x.device, dtype=torch.float64)
+    check(_lib.load().vt_instnorm_stats_nhwc(x.data_ptr(), _ptr(x2), mode, B, H * W, C, C, eps, stats.data_ptr(),
+                                             ws.data_ptr(), _stream()))
+    return stats
+
+
+def adain_apply(x: torch.Tensor, stats: torch.Tensor, gamma_beta: torch.Tensor, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(x, x2, stats, gamma_beta)
+    B, H, W, C = x.shape
+    mode = 0 if x2 is None else 1
+    Cs = C * (2 if mode else 1)
+    out = torch.empty((B, H, W, Cs), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_adain_apply_nhwc(x.data_ptr(), _ptr(x2), mode, B, H * W, C, C, stats.data_ptr(),
+                                          gamma_beta.contiguous().data_ptr(), out.data_ptr(), _round_flag(), _stream()))
+    return out
+
+
+def axpby(a: torch.Tensor, b: Optional[torch.Tensor], sa: float, sb: float = 0.0, round_tf32: Optional[bool] = None) -> torch.Tensor:
+    _req_cuda(a, b)
+    out = torch.empty_like(a)
+    rt = _round_flag() if round_tf32 is None else int(round_tf32)
+    check(_lib.load().vt_axpby_f32(a.data_ptr(), _ptr(b), out.data_ptr(), a.numel(), sa, sb, rt, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a11: frame transforms
+# ----------------------------------------------------------------------------------------------
+def frames_u8_to_f32(frames: torch.Tensor, out: Optional[torch.Tensor] = None, swap_rb: bool = False) -> torch.Tensor:
+    """uint8 ``[B,H,W,3]`` -> fp32 ``[B,3,H,W]`` in [-1,1] (ToTensor + Normalize(0.5,0.5))."""
+    if not frames.is_cuda or frames.dtype != torch.uint8:
+        raise _lib.VtError("frames_u8_to_f32 needs a CUDA uint8 tensor")
+    B, H, W, _ = frames.shape
+    if out is None:
+        out = torch.empty((B, 3, H, W), device=frames.device, dtype=torch.float32)
+    check(_lib.load().vt_frame_u8_to_f32(frames.contiguous().data_ptr(), out.data_ptr(), B, H, W, int(swap_rb),
+                                         out.stride(0), _stream()))
+    return out
+
+
+def f32_to_frames_u8(img: torch.Tensor, swap_rb: bool = True) -> torch.Tensor:
+    """fp32 ``[B,3,H,W]`` -> clamp(-1,1) -> uint8 ``[B,H,W,3]`` (util.tensor2cv2 semantics, RGB->BGR by default)."""
+    _req_cuda(img)
+    B, _, H, W = img.shape
+    out = torch.empty((B, H, W, 3), device=img.device, dtype=torch.uint8)
+    check(_lib.load().vt_f32_to_frame_u8(img.contiguous().data_ptr(), out.data_ptr(), B, H, W, int(swap_rb), _stream()))
+    return out

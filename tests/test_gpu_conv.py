@@ -1,0 +1,174 @@
+"""GPU parity of the convolution kernels: fp32 FFMA kernel vs the oracle's F.conv2d; tcgen05 kernel vs the FFMA kernel
+on TF32-representable data (where both must agree to fp32 accumulation-order noise), for every staging mode."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def maxerr(a, b):
+    assert tuple(a.shape) == tuple(b.shape), f"shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    return (a.double() - b.double()).abs().max().item()
+
+
+def tf32_exact(shape, g, scale=1.0):
+    """values with <= 8 significant bits: exactly representable in TF32 (10-bit mantissa)"""
+    return (torch.randint(-64, 65, shape, generator=g).float() / 32.0) * scale
+
+
+CASES = [
+    # B, Cin, Cout, H, W, k, stride, pad, dil
+    (1, 32, 32, 16, 8, 1, 1, 0, 1),      # exactly one tile, 1x1 == plain GEMM
+    (2, 32, 64, 16, 16, 3, 1, 1, 1),
+    (2, 64, 32, 19, 13, 3, 1, 1, 1),     # partial tiles
+    (1, 128, 256, 20, 12, 3, 1, 1, 1),
+    (1, 512, 512, 9, 16, 3, 1, 1, 1),    # two N tiles, 16 k-chunks
+    (2, 64, 64, 12, 20, 3, 1, 2, 2),     # dilation 2
+    (1, 64, 64, 24, 16, 3, 1, 4, 4),     # dilation 4
+    (2, 32, 64, 17, 21, 3, 2, 1, 1),     # stride 2 (parity views), odd sizes
+    (1, 64, 128, 32, 32, 3, 2, 1, 1),
+    (3, 32, 32, 4, 4, 3, 1, 1, 1),       # tiny maps (4x4 features of a 32x32 frame)
+]
+
+
+def _run(ops, x, w, bias, k, stride, pad, dil, precision, **epi):
+    xn = ops.to_nhwc(x.cuda(), round_tf32=False)
+    wp = ops.prep_weights(w.cuda(), cin_pad=xn.shape[3])
+    Ho = ops.conv_out_size(x.shape[2], k, stride, pad, dil)
+    Wo = ops.conv_out_size(x.shape[3], k, stride, pad, dil)
+    y = ops.conv2d_nhwc([xn], wp, ops.conv_taps(k, pad, dil), stride, Ho, Wo, bias=None if bias is None else bias.cuda(),
+                        precision=precision, **epi)
+    return ops.to_nchw(y).cpu()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_direct_vs_torch(case):
+    from vtoonify_b200 import ops
+    ops.set_precision("fp32")
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, stride=stride, padding=pad, dilation=dil)
+    y = _run(ops, x, w, b, k, stride, pad, dil, "fp32")
+    assert maxerr(y, ref) <= 5e-5, maxerr(y, ref)
+    ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("case", CASES)
+def test_tc_vs_direct_exact_data(case, mode):
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007)
+    x = tf32_exact((B, Cin, H, W), g)
+    w = tf32_exact((Cout, Cin, k, k), g, 1.0 / 8)
+    b = torch.randn(Cout, generator=g)
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32")
+    old = _lib.load().vt_set_option(b"tc_mode", mode)
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "tf32")
+    finally:
+        _lib.load().vt_set_option(b"tc_mode", old)
+        ops.set_precision("tf32")
+    scale = ref.abs().max().item()
+    assert maxerr(y, ref) <= 2e-5 * max(1.0, scale), f"mode {mode}: err {maxerr(y, ref):.3e} (scale {scale:.1f})"
+
+
+def test_tc_epilogue_variants():
+    from vtoonify_b200 import _lib, ops
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 2, 64, 18, 14
+    x = tf32_exact((B, C, H, W), g); w = tf32_exact((C, C, 3, 3), g, 1 / 8)
+    b = torch.randn(C, generator=g); res = torch.randn((B, C, H, W), generator=g)
+    noise = torch.randn((B, 1, H, W), generator=g); nw = torch.tensor([0.25])
+    ref = F.leaky_relu(F.conv2d(x, w, None, padding=1) + nw * noise + b.view(1, -1, 1, 1), 0.2) * 1.5
+    ref = ref * 0.7 + 0.3 * res
+    for prec in ("fp32", "tf32"):
+        ops.set_precision("fp32")  # no output rounding for this check
+        y = _run(ops, x, w, b, 3, 1, 1, 1, prec, noise=noise.cuda(), noise_w=nw.cuda(), act=_lib.ACT_LRELU, slope=0.2,
+                 gain=1.5, res=ops.to_nhwc(res.cuda(), round_tf32=False), alpha=0.7, beta=0.3)
+        assert maxerr(y, ref) <= 1e-4, (prec, maxerr(y, ref))
+    ops.set_precision("tf32")
+
+
+def test_virtual_concat_two_sources():
+    from vtoonify_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    a = tf32_exact((2, 64, 10, 9), g); c = tf32_exact((2, 32, 10, 9), g)
+    w = tf32_exact((64, 96, 3, 3), g, 1 / 8)
+    ref = F.conv2d(torch.cat([a, c], 1), w, padding=1)
+    for prec in ("fp32", "tf32"):
+        ops.set_precision("fp32")
+        wp = ops.prep_weights(w.cuda(), cin_pad=96)
+        y = ops.conv2d_nhwc([ops.to_nhwc(a.cuda(), round_tf32=False), ops.to_nhwc(c.cuda(), round_tf32=False)], wp,
+                            ops.conv_taps(3, 1), 1, 10, 9, precision=prec)
+        assert maxerr(ops.to_nchw(y).cpu(), ref) <= 1e-4, prec
+    ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_conv_transpose_polyphase(prec):
+    from vtoonify_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    x = tf32_exact((2, 64, 7, 9), g); w = tf32_exact((32, 64, 3, 3), g, 1 / 8)   # [Cout, Cin, k, k]
+    ref = F.conv_transpose2d(x, w.transpose(0, 1), stride=2, padding=0)
+    ops.set_precision("fp32")
+    wp = ops.prep_weights(w.cuda(), cin_pad=64)
+    y = ops.conv_transpose2d_s2_k3_nhwc(ops.to_nhwc(x.cuda(), round_tf32=False), wp, precision=prec)
+    ops.set_precision("tf32")
+    assert y.shape == (2, 15, 19, 32)
+    assert maxerr(ops.to_nchw(y).cpu(), ref) <= 1e-4
+
+
+def test_tf32_random_data_error_budget():
+    """Random (non-representable) data: TF32 error stays within the analytic budget 2^-11-ish relative to output rms."""
+    from vtoonify_b200 import ops
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn((2, 256, 24, 16), generator=g); w = torch.randn((256, 256, 3, 3), generator=g) / 48
+    ref = F.conv2d(x, w, padding=1)
+    ops.set_precision("tf32")
+    xn = ops.to_nhwc(x.cuda())
+    y = ops.conv2d_nhwc([xn], ops.prep_weights(w.cuda(), cin_pad=256), ops.conv_taps(3, 1), 1, 24, 16)
+    err = maxerr(ops.to_nchw(y).cpu(), ref)
+    rms = ref.pow(2).mean().sqrt().item()
+    print(f"tf32 conv 256->256: max err {err:.3e}, rms {rms:.3f}, rel {err / rms:.3e}")
+    assert err <= 4e-3 * rms
+
+
+def test_smalln_conv_variants():
+    from vtoonify_b200 import _lib, ops
+    from oracle import vt_oracle as O
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(15)
+    B, C, H, W = 2, 64, 10, 12
+    x = torch.randn((B, C, H, W), generator=g); skip3 = torch.randn((B, 3, H, W), generator=g)
+    w = torch.randn((3, C + 3, 3, 3), generator=g) / 24; b = torch.randn(3, generator=g)
+    ref = F.conv2d(torch.cat([skip3, x], 1), w, b, padding=1)
+    xn = ops.to_nhwc(x.cuda())
+    wp = ops.prep_weights(w[:, 3:].contiguous().cuda(), cin_pad=C)
+    wpl = w[:, :3].permute(2, 3, 0, 1).reshape(9, 3, 3).contiguous().cuda()
+    y = ops.smalln_conv(xn, wp, ops.conv_taps(3, 1), 3, B, H, W, planar=skip3.cuda(), planar_weight=wpl, bias=b.cuda())
+    assert maxerr(y.cpu(), ref) <= 2e-5
+    # mask head: tanh(relu(conv)) and fused f_E * m
+    w1 = torch.randn((1, C, 3, 3), generator=g) / 24; b1 = torch.randn(1, generator=g)
+    fe = torch.randn((B, 32, H, W), generator=g)
+    m_ref = torch.tanh(F.relu(F.conv2d(x, w1, b1, padding=1)))
+    m, fem = ops.smalln_conv(xn, ops.prep_weights(w1.cuda(), cin_pad=C), ops.conv_taps(3, 1), 1, B, H, W, bias=b1.cuda(),
+                             act=_lib.ACT_RELU_TANH, mul_src=ops.to_nhwc(fe.cuda()))
+    assert maxerr(m.cpu(), m_ref) <= 2e-5
+    assert maxerr(ops.to_nchw(fem).cpu(), fe * m_ref) <= 2e-5
+    # 1x1 + skip upsample (ToRGB tail)
+    w2 = torch.randn((3, C, 1, 1), generator=g) / 8
+    sk = torch.randn((B, 3, H // 2, W // 2), generator=g)
+    k4 = O.make_kernel([1, 3, 3, 1]) * 4
+    ref2 = F.conv2d(x, w2, b) + O.upfirdn2d(sk, k4, up=2, pad=(2, 1))
+    y2 = ops.smalln_conv(xn, ops.prep_weights(w2.cuda(), cin_pad=C), [(0, 0, 0)], 3, B, H, W, bias=b.cuda(),
+                         skip=sk.cuda(), skip_kernel=k4.cuda())
+    assert maxerr(y2.cpu(), ref2) <= 2e-5
+    ops.set_precision("tf32")

@@ -161,9 +161,11 @@ int vt_fir_nhwc_f32(const float* in, const float* kernel, float* out, int B, int
 
 /* ---- a7: instance-norm statistics + AdaIN apply (NHWC) ------------------------------------ */
 /* mode 0: x = in[b,p,c] (c < C). mode 1: virtual cat(in, |in - in2|) with 2C channels.
- * stats: [B, Cs, 2] = (mean, rstd) with biased variance, eps inside rsqrt; ws: >= B*Cs*2 doubles, zeroed by the call */
+ * stats: [B, Cs, 2] = (mean, rstd) with biased variance, eps inside rsqrt.  Deterministic two-stage reduction (no
+ * atomics); ws: caller-allocated scratch of vt_instnorm_ws_bytes() bytes. */
+int64_t vt_instnorm_ws_bytes(int B, int64_t HW, int C, int mode);
 int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
-                           float eps, float* stats, double* ws, void* stream);
+                           float eps, float* stats, void* ws, void* stream);
 /* out[b,p,c] = gamma[b,c] * (x - mean) * rstd + beta[b,c]; gamma_beta: [B, 2*Cs] (gamma then beta) */
 int vt_adain_apply_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
                         const float* stats, const float* gamma_beta, float* out, int round_tf32, void* stream);

@@ -59,7 +59,7 @@ def test_direct_vs_torch(case):
     ops.set_precision("tf32")
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("case", CASES)
 def test_tc_vs_direct_exact_data(case, mode):
     from vtoonify_b200 import _lib, ops

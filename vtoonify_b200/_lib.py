@@ -72,6 +72,7 @@ SYMBOLS = {
     "vt_smalln_conv_f32": (c_int, [POINTER(SmallNDesc), _P]),
     "vt_fir_nhwc_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int,
                                 c_float, c_float, c_int, _P]),
+    "vt_instnorm_ws_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),
     "vt_instnorm_stats_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, _P, _P, _P]),
     "vt_adain_apply_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, _P, _P, _P, c_int, _P]),
     "vt_axpby_f32": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_int, _P]),

@@ -40,7 +40,7 @@ struct TcArgs {
   CUtensorMap out_map;
   int n_src, kchunks[2], coff[2];
   int taps, tap_view[VT_MAX_TAPS], tap_vx[VT_MAX_TAPS], tap_vy[VT_MAX_TAPS], tap_w[VT_MAX_TAPS];
-  int halo, halo_x0, halo_y0, halo_w, base_offset_mode;
+  int halo, halo_x0, halo_y0, halo_w;
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int block_n, n_tiles, tiles_x, tiles_y, B, total_tiles, tmem_cols;
   int Ho, Wo, Cout, wB;
@@ -165,13 +165,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               tc_fence_after();
               uint32_t a_addr = a_base + sta * p.a_stage_bytes;
               uint32_t sbo = 1024;
-              uint32_t boff = 0;
               if (p.halo) {
+                // The 128B swizzle is a function of the absolute smem address bits (TMA wrote the halo box with the
+                // same function), so a tap is just a start address shifted by whole 128-byte rows; the descriptor's
+                // base-offset field stays 0 (setting it to (addr>>7)&7 was measured WRONG on B200).
                 a_addr += (uint32_t)(((p.tap_vy[t] - p.halo_y0) * p.halo_w + (p.tap_vx[t] - p.halo_x0)) * 128);
                 sbo = (uint32_t)p.halo_w * 128u;
-                if (p.base_offset_mode) boff = (a_addr >> 7) & 7u;
               }
-              const uint64_t adesc = make_smem_desc_sw128(a_addr, sbo, boff);
+              const uint64_t adesc = make_smem_desc_sw128(a_addr, sbo, 0);
               const uint64_t bdesc = make_smem_desc_sw128(b_base + stb * p.b_stage_bytes, 1024, 0);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -315,7 +316,7 @@ int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   return 0;
 }
 
-int g_tc_mode = 1;  // 0: one TMA box per tap; 1: halo box + shifted descriptors; 2: halo + base_offset field
+int g_tc_mode = 1;  // 0: one TMA box per tap; 1: one halo box per K chunk + row-shifted descriptors
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
 #define VT_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)
@@ -395,7 +396,6 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   const int halo_bytes = halo_w * halo_h * 128;
   a.halo = (g_tc_mode != 0) && d->stride == 1 && d->taps > 1 && halo_w <= 256 && halo_h <= 256 &&
            halo_bytes <= d->taps * TILE_M * 128 / 2 && halo_bytes <= 64 * 1024;
-  a.base_offset_mode = (g_tc_mode == 2);
   a.halo_x0 = dxmin; a.halo_y0 = dymin; a.halo_w = halo_w;
   a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
   a.a_stage_bytes = (int)(vt_cdiv(a.a_tx_bytes, 1024) * 1024);

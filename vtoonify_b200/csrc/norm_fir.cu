@@ -12,21 +12,21 @@
 
 namespace {
 
-// grid (chunks, B); dyn smem: Cs*2 floats
+// Deterministic two-stage reduction (no atomics): stage 1 — grid (chunks, B): every thread owns one float4 channel
+// group and every pstep-th pixel of its chunk, partials are combined across the pixel lanes in a fixed order through
+// shared memory and written to ws[chunk][b][Cs][2]; stage 2 sums the chunks in index order in double.
+// dyn smem: pstep * Cs * 2 floats.
 __global__ void __launch_bounds__(256)
 instnorm_partial_kernel(const float* __restrict__ in, const float* __restrict__ in2, int mode, int64_t HW, int C,
-                        int c_stride, int64_t chunk, double* __restrict__ ws) {
-  extern __shared__ float sacc[];  // [Cs][2]
+                        int c_stride, int64_t chunk, float* __restrict__ ws) {
+  extern __shared__ float sacc[];  // [pstep][Cs][2]
   const int Cs = mode ? 2 * C : C;
-  for (int i = threadIdx.x; i < Cs * 2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int b = blockIdx.y;
   const int nvec = C / 4;
   const int64_t p_begin = (int64_t)blockIdx.x * chunk;
   const int64_t p_end = (p_begin + chunk < HW) ? p_begin + chunk : HW;
   const float* ip = in + (int64_t)b * HW * c_stride;
   const float* ip2 = mode ? in2 + (int64_t)b * HW * c_stride : nullptr;
-  // each thread owns one float4 channel group `v` and every pstep-th pixel of the chunk
   const int pstep = blockDim.x / nvec;           // >= 1 (nvec <= 256 checked by the host)
   const int v = threadIdx.x % nvec, lane_p = threadIdx.x / nvec;
   if (lane_p < pstep) {
@@ -43,25 +43,37 @@ instnorm_partial_kernel(const float* __restrict__ in, const float* __restrict__ 
         for (int i = 0; i < 4; ++i) { const float d = fabsf(av[i] - ev[i]); s2[i] += d; q2[i] = fmaf(d, d, q2[i]); }
       }
     }
+    float* row = sacc + (size_t)lane_p * Cs * 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      atomicAdd(&sacc[(v * 4 + i) * 2 + 0], s[i]);
-      atomicAdd(&sacc[(v * 4 + i) * 2 + 1], q[i]);
+      row[(v * 4 + i) * 2 + 0] = s[i];
+      row[(v * 4 + i) * 2 + 1] = q[i];
       if (mode) {
-        atomicAdd(&sacc[(C + v * 4 + i) * 2 + 0], s2[i]);
-        atomicAdd(&sacc[(C + v * 4 + i) * 2 + 1], q2[i]);
+        row[(C + v * 4 + i) * 2 + 0] = s2[i];
+        row[(C + v * 4 + i) * 2 + 1] = q2[i];
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Cs * 2; i += blockDim.x) atomicAdd(&ws[(int64_t)b * Cs * 2 + i], (double)sacc[i]);
+  float* wrow = ws + ((int64_t)blockIdx.x * gridDim.y + b) * Cs * 2;
+  for (int i = threadIdx.x; i < Cs * 2; i += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < pstep; ++l) t += sacc[(size_t)l * Cs * 2 + i];
+    wrow[i] = t;
+  }
 }
 
-__global__ void instnorm_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int n, double inv_hw, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void instnorm_finalize_kernel(const float* __restrict__ ws, float* __restrict__ stats, int n, int chunks,
+                                         double inv_hw, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = b * Cs + c
   if (i >= n) return;
-  const double mean = ws[i * 2] * inv_hw;
-  double var = ws[i * 2 + 1] * inv_hw - mean * mean;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s += (double)ws[((int64_t)k * n + i) * 2];
+    q += (double)ws[((int64_t)k * n + i) * 2 + 1];
+  }
+  const double mean = s * inv_hw;
+  double var = q * inv_hw - mean * mean;
   if (var < 0) var = 0;
   stats[i * 2] = (float)mean;
   stats[i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
@@ -173,24 +185,39 @@ fir_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ kernel, 
 
 }  // namespace
 
+static void instnorm_plan(int64_t HW, int C, int64_t* chunk, int64_t* chunks) {
+  const int nvec = C / 4;
+  const int plan = 256 / nvec;                      // pixels processed concurrently by a block
+  int64_t ch = (int64_t)plan * 128;                 // ~128 pixels per thread
+  if (ch < 256) ch = 256;
+  *chunk = ch;
+  *chunks = vt_cdiv(HW, ch);
+}
+
+extern "C" int64_t vt_instnorm_ws_bytes(int B, int64_t HW, int C, int mode) {
+  if (B < 1 || HW < 1 || C < 4 || C % 4 || C / 4 > 256) return -1;
+  int64_t chunk, chunks;
+  instnorm_plan(HW, C, &chunk, &chunks);
+  return chunks * B * (mode ? 2 * C : C) * 2 * (int64_t)sizeof(float);
+}
+
 extern "C" int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
-                                      float eps, float* stats, double* ws, void* stream) {
+                                      float eps, float* stats, void* ws, void* stream) {
   VT_CHECK(in && stats && ws && (mode == 0 || (mode == 1 && in2)), "instnorm_stats: bad pointers/mode");
   VT_CHECK(B >= 1 && B <= 65535 && HW >= 1 && C >= 4 && C % 4 == 0 && c_stride >= C && c_stride % 4 == 0, "instnorm_stats: bad shape");
   VT_CHECK(C / 4 <= 256, "instnorm_stats: C must be <= 1024");
   const int Cs = mode ? 2 * C : C;
   cudaStream_t st = (cudaStream_t)stream;
-  VT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)B * Cs * 2, st));
-  const int nvec = C / 4;
-  const int plan = 256 / nvec;                      // pixels processed concurrently by a block
-  int64_t chunk = (int64_t)plan * 128;              // ~128 pixels per thread
-  if (chunk < 256) chunk = 256;
-  int64_t chunks = vt_cdiv(HW, chunk);
+  int64_t chunk, chunks;
+  instnorm_plan(HW, C, &chunk, &chunks);
+  const int pstep = 256 / (C / 4);
   dim3 grid((unsigned)chunks, (unsigned)B);
-  instnorm_partial_kernel<<<grid, 256, (size_t)Cs * 2 * sizeof(float), st>>>(in, in2, mode, HW, C, c_stride, chunk, ws);
+  instnorm_partial_kernel<<<grid, 256, (size_t)pstep * Cs * 2 * sizeof(float), st>>>(in, in2, mode, HW, C, c_stride, chunk,
+                                                                                    (float*)ws);
   VT_LAUNCH_CHECK();
   const int n = B * Cs;
-  instnorm_finalize_kernel<<<(unsigned)vt_cdiv(n, 256), 256, 0, st>>>(ws, stats, n, 1.0 / (double)HW, eps);
+  instnorm_finalize_kernel<<<(unsigned)vt_cdiv(n, 128), 128, 0, st>>>((const float*)ws, stats, n, (int)chunks,
+                                                                    1.0 / (double)HW, eps);
   VT_LAUNCH_CHECK();
   return 0;
 }

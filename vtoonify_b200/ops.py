@@ -31,6 +31,17 @@ def get_precision() -> str:
     return _precision
 
 
+# Optional per-launch timing of the tensor-core convolution (bench.py's roofline leg): when set to a list, every
+# vt_conv2d_tc_tf32 launch appends (start_event, end_event, algorithmic_flops, algorithmic_bytes, label).
+_tc_profile = None
+
+
+def set_tc_profile(sink):
+    global _tc_profile
+    old, _tc_profile = _tc_profile, sink
+    return old
+
+
 def _round_flag() -> int:
     return 1 if _precision == "tf32" else 0
 
@@ -165,7 +176,7 @@ def _pad32(c: int) -> int:
 
 
 def prep_weights(W: torch.Tensor, style: Optional[torch.Tensor] = None, scale: float = 1.0, demodulate: bool = False,
-                 cin_pad: Optional[int] = None) -> torch.Tensor:
+                 cin_pad: Optional[int] = None, round_tf32: Optional[bool] = None) -> torch.Tensor:
     """``W`` [Cout,Cin,kh,kw] (+ optional per-sample ``style`` [B,Cin]) -> conv-kernel layout
     ``[wB, kh*kw, Cout, cin_pad]`` = (scale*W)*style*demod (model/stylegan/model.py:259-267)."""
     _req_cuda(W, style)
@@ -175,7 +186,8 @@ def prep_weights(W: torch.Tensor, style: Optional[torch.Tensor] = None, scale: f
     out = torch.empty((wB, kh * kw, Cout, cin_pad), device=W.device, dtype=torch.float32)
     check(_lib.load().vt_modulate_weights_f32(W.contiguous().data_ptr(), _ptr(None if style is None else style.contiguous()),
                                               out.data_ptr(), wB, Cout, Cin, kh, kw, cin_pad, float(scale),
-                                              int(demodulate), _round_flag(), _stream()))
+                                              int(demodulate), _round_flag() if round_tf32 is None else int(round_tf32),
+                                              _stream()))
     return out
 
 
@@ -241,7 +253,17 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     d.round_tf32 = _round_flag()
     lib = _lib.load()
     if prec == "tf32" and lib.vt_conv2d_tc_supported(d):
-        check(lib.vt_conv2d_tc_tf32(d, _stream()))
+        if _tc_profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cin = sum(int(d.src_c[i]) for i in range(d.n_src))
+            flops = 2.0 * B * Ho * Wo * Cout * cin * len(taps)
+            nbytes = 4.0 * (B * H * W * cin + B * Ho * Wo * Cout + weight.numel())
+            e0.record()
+            check(lib.vt_conv2d_tc_tf32(d, _stream()))
+            e1.record()
+            _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout} k{len(taps)} s{stride} {H}x{W}"))
+        else:
+            check(lib.vt_conv2d_tc_tf32(d, _stream()))
     else:
         check(lib.vt_conv2d_direct_f32(d, _stream()))
     return out
@@ -340,7 +362,10 @@ def instnorm_stats(x: torch.Tensor, x2: Optional[torch.Tensor] = None, eps: floa
     mode = 0 if x2 is None else 1
     Cs = C * (2 if mode else 1)
     stats = torch.empty((B, Cs, 2), device=x.device, dtype=torch.float32)
-    ws = torch.empty((B * Cs * 2,), device=x.device, dtype=torch.float64)
+    nbytes = _lib.load().vt_instnorm_ws_bytes(B, H * W, C, mode)
+    if nbytes < 0:
+        raise _lib.VtError(f"instnorm_stats: unsupported shape C={C}")
+    ws = torch.empty((nbytes // 4,), device=x.device, dtype=torch.float32)
     check(_lib.load().vt_instnorm_stats_nhwc(x.data_ptr(), _ptr(x2), mode, B, H * W, C, C, eps, stats.data_ptr(),
                                              ws.data_ptr(), _stream()))
     return stats

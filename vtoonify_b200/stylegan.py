@@ -90,10 +90,10 @@ class _PreppedWeight:
         self.key = None
         self.value = None
 
-    def get(self, weight, scale, cin_pad):
-        key = (weight.data_ptr(), weight._version, float(scale), cin_pad, ops.get_precision(), weight.device)
+    def get(self, weight, scale, cin_pad, round_tf32=None):
+        key = (weight.data_ptr(), weight._version, float(scale), cin_pad, ops.get_precision(), weight.device, round_tf32)
         if key != self.key:
-            self.value = ops.prep_weights(weight.detach(), None, scale, False, cin_pad)
+            self.value = ops.prep_weights(weight.detach(), None, scale, False, cin_pad, round_tf32=round_tf32)
             self.key = key
         return self.value
 
@@ -187,11 +187,11 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def modulated_weights(self, style, cin_pad, externalweight=None):
+    def modulated_weights(self, style, cin_pad, externalweight=None, round_tf32=None):
         """[B, k*k, Cout, cin_pad] = scale * (W [+ ext]) * s[b] * demod[b]  (model.py:259-267)."""
         s = self.modulation(style)
         W = self.weight[0] if externalweight is None else (self.weight + externalweight)[0]
-        return ops.prep_weights(W.detach(), s, self.scale, self.demodulate, cin_pad)
+        return ops.prep_weights(W.detach(), s, self.scale, self.demodulate, cin_pad, round_tf32=round_tf32)
 
     def forward_nhwc(self, x, style, externalweight=None, bias=None, noise=None, noise_w=None, act=False,
                      slope=0.2, gain=ops.SQRT2):
@@ -219,7 +219,7 @@ class ModulatedConv2d(nn.Module):
         C = input.shape[1]
         x = ops.to_nhwc(input, ops._pad32(C) if C % 32 else None)
         if self.out_channel <= 4 and self.kernel_size == 1 and not (self.upsample or self.downsample):
-            w = self.modulated_weights(style, x.shape[3], externalweight)
+            w = self.modulated_weights(style, x.shape[3], externalweight, round_tf32=False)
             B, H, W, _ = x.shape
             return ops.smalln_conv(x, w, [(0, 0, 0)], self.out_channel, B, H, W)
         return ops.nhwc_as_nchw_view(self.forward_nhwc(x, style, externalweight))
@@ -302,7 +302,7 @@ class ToRGB(nn.Module):
     def forward_nhwc(self, x, style, skip=None, externalweight=None):
         """x NHWC -> planar NCHW [B,3,H,W] (+ fused skip upsample/add)."""
         B, H, W, Cs = x.shape
-        w = self.conv.modulated_weights(style, Cs, externalweight)
+        w = self.conv.modulated_weights(style, Cs, externalweight, round_tf32=False)   # CUDA-core kernel: keep fp32
         fuse = (skip is not None and self.upsample.factor == 2 and tuple(self.upsample.kernel.shape) == (4, 4)
                 and self.upsample.pad == (2, 1) and skip.shape[2] * 2 == H and skip.shape[3] * 2 == W)
         out = ops.smalln_conv(x, w, [(0, 0, 0)], 3, B, H, W, bias=self.bias.view(3),

@@ -61,7 +61,7 @@ class Conv2d(nn.Module):
             self._w_nhwc_part = wt[:, npl:].contiguous()
             self._w_planar = wt[:, :npl].permute(2, 3, 0, 1).reshape(k * k, wt.shape[0], npl).contiguous() if npl else None
             self._split_key = key
-        w = self._wp.get(self._w_nhwc_part, 1.0, Cs)
+        w = self._wp.get(self._w_nhwc_part, 1.0, Cs, round_tf32=False)
         return ops.smalln_conv(x, w, ops.conv_taps(k, self.padding), self.weight.shape[0], B, H, W, planar=planar,
                                planar_weight=self._w_planar, bias=self.bias, act=act, mul_src=mul_src)
 

@@ -79,8 +79,16 @@ int vt_pixelnorm_f32(const float* in, float* out, int rows, int dim, void* strea
 int vt_modulate_weights_f32(const float* W, const float* style, float* out, int wB, int Cout, int Cin, int kh, int kw,
                             int cin_pad, float scale, int demodulate, int round_tf32, void* stream);
 
+/* Fold Blur(4x4, pad (1,1)) o conv_transpose2d(stride 2, 3x3) into 4 phase-specific 3x3 kernels:
+ * w: [wB][9][Cout][cpad] (slab ky*3+kx, already modulated/demodulated), blur: [4,4] device,
+ * out: [wB][9][4*Cout][cpad], slab = (dy+1)*3 + (dx+1), row = phase*Cout + n, phase = ry*2+rx (the 4 phases are stacked
+ * along the GEMM N dimension):  out[2q+ry, 2p+rx] = sum_{dy,dx} x[q+dy, p+dx] * G[dy][dx][phase].
+ * model/stylegan/model.py:273-286 (conv_transpose2d then self.blur). */
+int vt_fold_upconv_weights_f32(const float* w, const float* blur, float* out, int wB, int Cout, int cpad, int round_tf32,
+                               void* stream);
+
 /* ---- convolution descriptor (NHWC activations) -------------------------------------------- */
-#define VT_MAX_TAPS 9
+#define VT_MAX_TAPS 36     /* 9 taps x up to 4 output phases (folded up-conv) */
 #define VT_ACT_NONE 0
 #define VT_ACT_LRELU 1      /* lrelu(slope) * gain                                             */
 #define VT_ACT_RELU_TANH 2  /* tanh(relu(v))      (Fusion mask, model/vtoonify.py:126)          */
@@ -98,6 +106,11 @@ typedef struct vt_conv_desc {
   int32_t tap_dy[VT_MAX_TAPS];
   int32_t tap_dx[VT_MAX_TAPS];
   int32_t tap_w[VT_MAX_TAPS];   /* index of the weight slab used by tap t                        */
+  int32_t tap_phase[VT_MAX_TAPS]; /* reserved (must be 0)                                          */
+  int32_t n_phase;              /* 1, or 4: weight rows are phase-major [n_phase*Cout] per tap and phase ph's Cout
+                                   outputs go to the strided view at phase_off[ph] (folded stride-2 up-conv)       */
+  int32_t out_cpitch;           /* floats per pixel of the dense tensor `out` points into (noise index = offset / out_cpitch) */
+  int64_t phase_off[4];         /* element offset of each phase's strided output view             */
   const float* weight;          /* [wB][w_taps][Cout][w_cstride]; channel order = src0 then src1 */
   int32_t wB;                   /* 1 (shared) or B (per-sample, modulated)                       */
   int32_t w_taps;               /* slabs per sample in `weight`                                  */
@@ -105,9 +118,10 @@ typedef struct vt_conv_desc {
   int32_t Cout;
   float*  out;                  /* strided NHWC view: out[b*out_sb + oy*out_sy + ox*out_sx + n]  */
   int64_t out_sb, out_sy, out_sx;   /* element strides                                           */
-  /* epilogue: v = acc + bias[n] + noise_w[0]*noise[b,oy,ox]; v = act(v); v = v*alpha + beta*res */
+  /* epilogue: v = acc + bias[n] + noise_w[0]*noise[pixel]; v = act(v); v = v*alpha + beta*res
+   * with pixel = (phase_off[ph] + b*out_sb + oy*out_sy + ox*out_sx) / out_cpitch                    */
   const float* bias;            /* [Cout] or NULL                                                */
-  const float* noise;           /* [B, Ho, Wo] planar or NULL                                    */
+  const float* noise;           /* planar [B, H_dense, W_dense] over the dense output tensor, or NULL */
   const float* noise_w;         /* device scalar or NULL                                         */
   int32_t act;                  /* VT_ACT_*                                                      */
   float   slope, gain;          /* lrelu params                                                  */
@@ -125,6 +139,8 @@ int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream);
 int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 accepts the descriptor */
 /* tuning knobs for experiments: key in {"tc_mode"}; returns previous value */
 int vt_set_option(const char* key, int value);
+/* tuning only: device buffer of 148*16 uint64 that conv_tc fills with per-role wait-cycle counters (NULL disables) */
+int vt_set_debug_buffer(void* dev_ptr);
 
 /* ---- small-N conv (Cout <= 4): planar output, optional planar extra source + skip upsample */
 typedef struct vt_smalln_desc {
@@ -180,7 +196,9 @@ int vt_frame_u8_to_f32(const uint8_t* in, float* out, int B, int H, int W, int s
 /* fp32 NCHW (3ch) -> clamp(-1,1) -> ((v+1)*127.5) truncated to u8, HWC, optional RGB->BGR ; util.py:190-192 */
 int vt_f32_to_frame_u8(const float* in, uint8_t* out, int B, int H, int W, int swap_rb, void* stream);
 
-/* ---- tcgen05/TMA self-test kernels (used by tests/ only; tiny GEMMs that validate descriptors) */
+/* ---- tcgen05 issue-rate microbenchmark (tools/ only): D[0] = average SM cycles per tcgen05.mma (M=128, N, K=8 tf32)
+ * over K*4 MMAs on resident smem operands. variant bit0: alternate 2 accumulators, bit1: converged-warp issue,
+ * bit2: commit+wait per 4 MMAs. A, B, M unused. */
 int vt_selftest_tc_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, int variant, void* stream);
 
 #ifdef __cplusplus

@@ -172,3 +172,55 @@ def test_smalln_conv_variants():
                          skip=sk.cuda(), skip_kernel=k4.cuda())
     assert maxerr(y2.cpu(), ref2) <= 2e-5
     ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("mt", [1, 2, 4])
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3], CASES[5], CASES[9]])
+def test_tc_m_tiles_per_work_item(case, mt):
+    """Work items of 1/2/4 M tiles sharing each weight tile must give the same result as the FFMA kernel."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007)
+    x = tf32_exact((B, Cin, H, W), g)
+    w = tf32_exact((Cout, Cin, k, k), g, 1.0 / 8)
+    b = torch.randn(Cout, generator=g)
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32")
+    old = _lib.load().vt_set_option(b"tc_mt", mt)
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "tf32")
+    finally:
+        _lib.load().vt_set_option(b"tc_mt", old)
+        ops.set_precision("tf32")
+    scale = ref.abs().max().item()
+    assert maxerr(y, ref) <= 2e-5 * max(1.0, scale), f"mt {mt}: err {maxerr(y, ref):.3e} (scale {scale:.1f})"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 7, 9), (1, 128, 64, 16, 24), (2, 32, 32, 33, 20), (1, 512, 256, 8, 8)])
+def test_folded_upconv(shape):
+    """Blur o conv_transpose2d folded into 4 phase kernels (one launch) vs the two-step reference formulation."""
+    from vtoonify_b200 import ops
+    from oracle import vt_oracle as O
+    B, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = tf32_exact((B, Cin, H, W), g)
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) / np.sqrt(Cin * 9)
+    k4 = O.make_kernel([1, 3, 3, 1]) * 4
+    bias = torch.randn(Cout, generator=g); noise = torch.randn((B, 1, 2 * H, 2 * W), generator=g); nw = torch.tensor([0.2])
+    ref = O.upfirdn2d(F.conv_transpose2d(x, w.transpose(0, 1), stride=2), k4, pad=(1, 1))
+    ref = F.leaky_relu(ref + nw * noise + bias.view(1, -1, 1, 1), 0.2) * 1.4142135
+    xn = ops.to_nhwc(x.cuda(), round_tf32=False)
+    # fp32: FFMA kernel on un-rounded folded weights == the reference to fp32 noise
+    ops.set_precision("fp32")
+    wf = ops.fold_upconv_weights(ops.prep_weights(w.cuda(), cin_pad=Cin), k4.cuda())
+    y32 = ops.conv_up2_folded_nhwc(xn, wf, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135)
+    assert maxerr(ops.to_nchw(y32).cpu(), ref) <= 2e-5 * max(1.0, ref.abs().max().item())
+    # tf32: tensor-core kernel vs FFMA kernel on the SAME TF32-rounded folded weights
+    ops.set_precision("tf32")
+    wfr = ops.fold_upconv_weights(ops.prep_weights(w.cuda(), cin_pad=Cin, round_tf32=False), k4.cuda())
+    ops.set_precision("fp32")   # no output rounding in either run
+    a = ops.conv_up2_folded_nhwc(xn, wfr, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135, precision="fp32")
+    t = ops.conv_up2_folded_nhwc(xn, wfr, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135, precision="tf32")
+    ops.set_precision("tf32")
+    assert maxerr(ops.to_nchw(t).cpu(), ops.to_nchw(a).cpu()) <= 2e-5 * max(1.0, ref.abs().max().item())
+    assert maxerr(ops.to_nchw(t).cpu(), ref) <= 5e-3 * max(1.0, ref.abs().max().item())

@@ -1,0 +1,56 @@
+"""Per-role wait-cycle breakdown of conv_tc_kernel for selected layer shapes (tuning aid).
+   python tools/tc_role_timing.py            (on the GPU box)"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vtoonify_b200 import _lib, ops
+
+lib = _lib.load()
+dev = torch.device("cuda:0")
+dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+K4 = (torch.tensor([1., 3., 3., 1.])[:, None] * torch.tensor([1., 3., 3., 1.])[None, :] / 64 * 4).to(dev)
+
+
+def report(name, fn, flops):
+    fn(); torch.cuda.synchronize()
+    dbg.zero_()
+    lib.vt_set_debug_buffer(dbg.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    lib.vt_set_debug_buffer(None)
+    d = dbg.view(148, 16).double()
+    ms = e0.elapsed_time(e1)
+    tot = d[:, 0].mean().item()
+    def pct(i): return 100 * d[:, i].mean().item() / max(tot, 1)
+    print(f"{name:34s} {ms:7.3f} ms {flops / ms / 1e9:6.0f} TF/s | cycles/CTA {tot:9.0f} | producer waits: A-empty {pct(1):4.1f}% B-empty {pct(2):4.1f}% "
+          f"| mma waits: A-full {pct(6):4.1f}% B-full {pct(7):4.1f}% tmem-empty {pct(8):4.1f}% "
+          f"| epi waits: tmem-full {pct(11):4.1f}% store-read {pct(12):4.1f}% bar {pct(13):4.1f}%")
+
+
+def conv_case(B, Cin, Cout, H, W, k=3, dil=1):
+    x = torch.randn((B, H, W, Cin), device=dev)
+    w = ops.prep_weights(torch.randn((Cout, Cin, k, k), device=dev) / (3 * Cin ** 0.5), cin_pad=Cin)
+    bias = torch.zeros(Cout, device=dev)
+    pad = dil * (k // 2)
+    fn = lambda: ops.conv2d_nhwc([x], w, ops.conv_taps(k, pad, dil), 1, H, W, bias=bias, act=1)
+    report(f"{Cin}->{Cout} k{k} d{dil} {H}x{W} B{B}", fn, 2.0 * B * H * W * Cout * Cin * k * k)
+
+
+def up_case(B, Cin, Cout, H, W):
+    x = torch.randn((B, H, W, Cin), device=dev)
+    w9 = ops.prep_weights(torch.randn((Cout, Cin, 3, 3), device=dev) / (3 * Cin ** 0.5), cin_pad=Cin, round_tf32=False)
+    wf = ops.fold_upconv_weights(w9, K4)
+    bias = torch.zeros(Cout, device=dev)
+    fn = lambda: ops.conv_up2_folded_nhwc(x, wf, bias=bias, act=1)
+    report(f"up {Cin}->{Cout} {H}x{W} B{B}", fn, 2.0 * B * H * W * Cout * Cin * 36)
+
+
+with torch.no_grad():
+    conv_case(4, 512, 512, 72, 128)
+    conv_case(4, 256, 256, 288, 512)
+    conv_case(4, 128, 128, 576, 1024)
+    conv_case(4, 64, 64, 1152, 2048)
+    conv_case(4, 32, 32, 2304, 4096)
+    up_case(4, 64, 32, 1152, 2048)
+    up_case(4, 128, 64, 576, 1024)
+    up_case(4, 512, 256, 144, 256)

@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvtoonify_b200.so")
-VT_MAX_TAPS = 9
+VT_MAX_TAPS = 36
 ACT_NONE, ACT_LRELU, ACT_RELU_TANH = 0, 1, 2
 
 
@@ -25,6 +25,7 @@ class ConvDesc(Structure):
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("Ho", c_int32), ("Wo", c_int32),
         ("stride", c_int32), ("taps", c_int32),
         ("tap_dy", c_int32 * VT_MAX_TAPS), ("tap_dx", c_int32 * VT_MAX_TAPS), ("tap_w", c_int32 * VT_MAX_TAPS),
+        ("tap_phase", c_int32 * VT_MAX_TAPS), ("n_phase", c_int32), ("out_cpitch", c_int32), ("phase_off", c_int64 * 4),
         ("weight", c_void_p), ("wB", c_int32), ("w_taps", c_int32), ("w_cstride", c_int32), ("Cout", c_int32),
         ("out", c_void_p), ("out_sb", c_int64), ("out_sy", c_int64), ("out_sx", c_int64),
         ("bias", c_void_p), ("noise", c_void_p), ("noise_w", c_void_p),
@@ -65,10 +66,12 @@ SYMBOLS = {
     "vt_linear_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_int, _P]),
     "vt_pixelnorm_f32": (c_int, [_P, _P, c_int, c_int, _P]),
     "vt_modulate_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
+    "vt_fold_upconv_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vt_conv2d_direct_f32": (c_int, [POINTER(ConvDesc), _P]),
     "vt_conv2d_tc_tf32": (c_int, [POINTER(ConvDesc), _P]),
     "vt_conv2d_tc_supported": (c_int, [POINTER(ConvDesc)]),
     "vt_set_option": (c_int, [c_char_p, c_int]),
+    "vt_set_debug_buffer": (c_int, [_P]),
     "vt_smalln_conv_f32": (c_int, [POINTER(SmallNDesc), _P]),
     "vt_fir_nhwc_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int,
                                 c_float, c_float, c_int, _P]),
@@ -100,6 +103,9 @@ def load():
         fn.argtypes = args
     if lib.vt_abi_version() != 1:
         raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects 1")
+    for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup")):
+        if os.environ.get(env):
+            lib.vt_set_option(key, int(os.environ[env]))      # tuning experiments only
     _lib = lib
     return lib
 

@@ -22,6 +22,8 @@ constexpr int LDA = BM + 4, LDB = BN + 4;
 
 struct DirectArgs {
   vt_conv_desc d;
+  int w_rows;   // weight rows per tap slab (n_phase * Cout)
+  int w_row0;   // first row of this launch's phase
 };
 
 __global__ void __launch_bounds__(256)
@@ -64,7 +66,7 @@ conv_direct_kernel(const __grid_constant__ DirectArgs args) {
       const int ix = lox * d.stride + d.tap_dx[t];
       const bool pix_ok = lm_ok && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
       const float* ap = sp + (((int64_t)b * d.H + iy) * d.W + ix) * scs;
-      const float* wp = d.weight + (((int64_t)wb * d.w_taps + d.tap_w[t]) * d.Cout + ln) * d.w_cstride + coff;
+      const float* wp = d.weight + (((int64_t)wb * d.w_taps + d.tap_w[t]) * args.w_rows + args.w_row0 + ln) * d.w_cstride + coff;
       for (int c0 = 0; c0 < sc; c0 += BK) {
         const int c = c0 + lk;
         float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -97,8 +99,8 @@ conv_direct_kernel(const __grid_constant__ DirectArgs args) {
     const int64_t m = m0 + ty * 4 + i;
     if (m >= HoWo) continue;
     const int oy = (int)(m / d.Wo), ox = (int)(m % d.Wo);
-    const int64_t off = (int64_t)b * d.out_sb + (int64_t)oy * d.out_sy + (int64_t)ox * d.out_sx;
-    const float nz = d.noise ? nw * d.noise[(int64_t)b * HoWo + m] : 0.f;
+    const int64_t off = d.phase_off[0] + (int64_t)b * d.out_sb + (int64_t)oy * d.out_sy + (int64_t)ox * d.out_sx;
+    const float nz = d.noise ? nw * d.noise[off / d.out_cpitch] : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -148,61 +150,81 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
   if (d.skip && threadIdx.x < 16) Ks[threadIdx.x] = d.skip_kernel[threadIdx.x];
   __syncthreads();
 
+  // A warp owns 32 consecutive pixels.  They are processed 4 at a time (8 lanes x float4 = 32 channels of one pixel per
+  // load instruction, fully coalesced); the 4 reduced results of sub-iteration `it` are handed to lanes 4*it..4*it+3 so
+  // that afterwards lane L holds pixel L's outputs and every planar store / skip read is a coalesced 128-byte access.
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7;      // channel slice
-  const int grp = lane >> 3;     // pixel within the warp's group of 4
+  const int grp = lane >> 3;     // pixel within the sub-iteration
   const int warp = threadIdx.x >> 5;
   const int64_t HW = (int64_t)d.H * d.W;
-  const int64_t groups = vt_cdiv(HW, 4);
+  const int64_t runs = vt_cdiv(HW, 32);
   const int hs = d.H / 2, ws = d.W / 2;
-  for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < groups; g += (int64_t)gridDim.x * 8) {
-    const int64_t p = g * 4 + grp;
-    const bool p_ok = p < HW;
-    const int y = p_ok ? (int)(p / d.W) : 0, x = p_ok ? (int)(p % d.W) : 0;
-    float acc[N];
+  for (int64_t run = (int64_t)blockIdx.x * 8 + warp; run < runs; run += (int64_t)gridDim.x * 8) {
+    const int64_t p0 = run * 32;
+    float keep[N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) acc[n] = 0.f;
-    if (p_ok && d.src_c > 0) {
-      for (int t = 0; t < d.taps; ++t) {
-        const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
-        if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
-        const float* ap = d.src + (((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride;
-        const float* wt = Ws + (size_t)t * N * d.src_c;
-        for (int c = sub * 4; c < d.src_c; c += 32) {
-          const float4 a = *reinterpret_cast<const float4*>(ap + c);
+    for (int n = 0; n < N; ++n) keep[n] = 0.f;
+    if (d.src_c > 0) {
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int64_t p = p0 + it * 4 + grp;
+        const bool p_ok = p < HW;
+        const int y = p_ok ? (int)(p / d.W) : 0, x = p_ok ? (int)(p % d.W) : 0;
+        float acc[N];
 #pragma unroll
-          for (int n = 0; n < N; ++n) {
-            const float4 w = *reinterpret_cast<const float4*>(wt + n * d.src_c + c);
-            acc[n] = fmaf(a.x, w.x, acc[n]);
-            acc[n] = fmaf(a.y, w.y, acc[n]);
-            acc[n] = fmaf(a.z, w.z, acc[n]);
-            acc[n] = fmaf(a.w, w.w, acc[n]);
+        for (int n = 0; n < N; ++n) acc[n] = 0.f;
+        if (p_ok) {
+          for (int t = 0; t < d.taps; ++t) {
+            const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+            if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+            const float* ap = d.src + (((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride;
+            const float* wt = Ws + (size_t)t * N * d.src_c;
+            for (int c = sub * 4; c < d.src_c; c += 32) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(ap + c));
+#pragma unroll
+              for (int n = 0; n < N; ++n) {
+                const float4 w = *reinterpret_cast<const float4*>(wt + n * d.src_c + c);
+                acc[n] = fmaf(a.x, w.x, acc[n]);
+                acc[n] = fmaf(a.y, w.y, acc[n]);
+                acc[n] = fmaf(a.z, w.z, acc[n]);
+                acc[n] = fmaf(a.w, w.w, acc[n]);
+              }
+            }
           }
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          float v = acc[n];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          // lane 4*it+g takes the result of group g (held by lanes 8g..8g+7)
+          const float r = __shfl_sync(0xffffffffu, v, (lane & 3) * 8);
+          if ((lane >> 2) == it) keep[n] = r;
         }
       }
     }
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
-      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
-      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
-    }
+    // ---- per-pixel epilogue: lane L <-> pixel p0 + L
+    const int64_t p = p0 + lane;
+    const bool p_ok = p < HW;
+    const int y = p_ok ? (int)(p / d.W) : 0, x = p_ok ? (int)(p % d.W) : 0;
     float m0v = 0.f;
-    if (p_ok && sub == 0) {
+    if (p_ok) {
       if (d.n_planar > 0) {
         for (int t = 0; t < d.taps; ++t) {
           const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
           if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
           for (int cp = 0; cp < d.n_planar; ++cp) {
-            const float a = d.planar[((int64_t)b * d.n_planar + cp) * HW + (int64_t)iy * d.W + ix];
+            const float a = __ldg(d.planar + ((int64_t)b * d.n_planar + cp) * HW + (int64_t)iy * d.W + ix);
 #pragma unroll
-            for (int n = 0; n < N; ++n) acc[n] = fmaf(a, Wp[(t * N + n) * d.n_planar + cp], acc[n]);
+            for (int n = 0; n < N; ++n) keep[n] = fmaf(a, Wp[(t * N + n) * d.n_planar + cp], keep[n]);
           }
         }
       }
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        float v = acc[n];
+        float v = keep[n];
         if (d.bias) v += d.bias[n];
         if (d.act == VT_ACT_RELU_TANH) v = tanhf(fmaxf(v, 0.f));
         if (d.skip) {
@@ -216,7 +238,7 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
             for (int kx = (tx & 1) ? 1 : 0; kx < 4; kx += 2) {
               const int ix = (tx + kx) >> 1;
               if (tx + kx < 0 || ix >= ws) continue;
-              u = fmaf(sp[(int64_t)iy * ws + ix], Ks[(3 - ky) * 4 + (3 - kx)], u);
+              u = fmaf(__ldg(sp + (int64_t)iy * ws + ix), Ks[(3 - ky) * 4 + (3 - kx)], u);
             }
           }
           v += u;
@@ -226,15 +248,18 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
       }
     }
     if (d.mul_out) {
-      m0v = __shfl_sync(0xffffffffu, m0v, grp * 8);
-      if (p_ok) {
-        const float* ms = d.mul_src + ((int64_t)b * HW + p) * d.mul_c;
-        float* mo = d.mul_out + ((int64_t)b * HW + p) * d.mul_c;
-        for (int c = sub * 4; c < d.mul_c; c += 32) {
-          float4 a = *reinterpret_cast<const float4*>(ms + c);
-          a.x *= m0v; a.y *= m0v; a.z *= m0v; a.w *= m0v;
-          if (d.round_tf32) { a.x = vt_round_tf32(a.x); a.y = vt_round_tf32(a.y); a.z = vt_round_tf32(a.z); a.w = vt_round_tf32(a.w); }
-          *reinterpret_cast<float4*>(mo + c) = a;
+      for (int it = 0; it < 8; ++it) {
+        const float m = __shfl_sync(0xffffffffu, m0v, it * 4 + grp);
+        const int64_t pp = p0 + it * 4 + grp;
+        if (pp < HW) {
+          const float* ms = d.mul_src + ((int64_t)b * HW + pp) * d.mul_c;
+          float* mo = d.mul_out + ((int64_t)b * HW + pp) * d.mul_c;
+          for (int c = sub * 4; c < d.mul_c; c += 32) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(ms + c));
+            a.x *= m; a.y *= m; a.z *= m; a.w *= m;
+            if (d.round_tf32) { a.x = vt_round_tf32(a.x); a.y = vt_round_tf32(a.y); a.z = vt_round_tf32(a.z); a.w = vt_round_tf32(a.w); }
+            *reinterpret_cast<float4*>(mo + c) = a;
+          }
         }
       }
     }
@@ -263,8 +288,12 @@ static int validate_conv_desc(const vt_conv_desc* d, const char* who) {
     ctot += d->src_c[s];
   }
   VT_CHECK(d->w_cstride >= ctot && d->w_cstride % 4 == 0 && aligned16(d->weight), "%s: bad weight stride/alignment", who);
-  for (int t = 0; t < d->taps; ++t)
+  VT_CHECK(d->n_phase == 1 || d->n_phase == 4, "%s: n_phase must be 1 or 4", who);
+  VT_CHECK(d->out_cpitch >= d->Cout, "%s: out_cpitch (%d) must be >= Cout", who, d->out_cpitch);
+  for (int t = 0; t < d->taps; ++t) {
     VT_CHECK(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "%s: tap_w[%d] out of range", who, t);
+    VT_CHECK(d->tap_phase[t] >= 0 && d->tap_phase[t] < d->n_phase, "%s: tap_phase[%d] out of range", who, t);
+  }
   VT_CHECK(d->act >= 0 && d->act <= 2, "%s: bad act", who);
   if (d->noise) VT_CHECK(d->noise_w != nullptr, "%s: noise without noise_w", who);
   return 0;
@@ -274,12 +303,18 @@ int vt_validate_conv_desc(const vt_conv_desc* d, const char* who) { return valid
 extern "C" int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream) {
   if (validate_conv_desc(d, "conv2d_direct")) return 1;
   VT_CHECK(d->B <= 65535 && vt_cdiv(d->Cout, BN) <= 65535, "conv2d_direct: grid too large");
-  DirectArgs a;
-  a.d = *d;
   const int64_t HoWo = (int64_t)d->Ho * d->Wo;
   dim3 grid((unsigned)vt_cdiv(HoWo, BM), (unsigned)vt_cdiv(d->Cout, BN), (unsigned)d->B);
-  conv_direct_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  VT_LAUNCH_CHECK();
+  for (int ph = 0; ph < d->n_phase; ++ph) {   // one launch per output phase (weight rows ph*Cout.., view offset phase_off[ph])
+    DirectArgs a;
+    a.d = *d;
+    a.w_rows = d->n_phase * d->Cout;
+    a.w_row0 = ph * d->Cout;
+    a.d.n_phase = 1;
+    a.d.phase_off[0] = d->phase_off[ph];
+    conv_direct_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    VT_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -308,8 +343,8 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   const size_t smem = ((size_t)d->taps * d->Cout * (d->src_c + d->n_planar) + 16) * sizeof(float);
   VT_CHECK(smem <= 200 * 1024, "smalln_conv: weights (%zu B) do not fit in shared memory", smem);
   const int64_t HW = (int64_t)d->H * d->W;
-  int64_t blocks = vt_cdiv(vt_cdiv(HW, 4), 8);
-  const int64_t cap = (int64_t)vt_num_sms() * 4;
+  int64_t blocks = vt_cdiv(vt_cdiv(HW, 32), 8);
+  const int64_t cap = (int64_t)vt_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)d->B);
   cudaStream_t st = (cudaStream_t)stream;

@@ -37,21 +37,30 @@ constexpr int MAX_SMEM = 227 * 1024;
 struct TcArgs {
   CUtensorMap in_map[2][4];
   CUtensorMap w_map;
-  CUtensorMap out_map;
+  CUtensorMap out_map[4];                      // one strided output view per phase
   int n_src, kchunks[2], coff[2];
-  int taps, tap_view[VT_MAX_TAPS], tap_vx[VT_MAX_TAPS], tap_vy[VT_MAX_TAPS], tap_w[VT_MAX_TAPS];
+  // "B steps": one weight tile (tap of one phase) each; every step feeds `mt` accumulators (the M tiles of the work item)
+  int n_steps;
+  int8_t step_view[VT_MAX_TAPS], step_vx[VT_MAX_TAPS], step_vy[VT_MAX_TAPS];
+  int16_t step_w[VT_MAX_TAPS];
+  int mt, n_phase, acc_stages;                 // mt accumulators (M tiles) of block_n columns per work item; n_phase: the N
+                                               // dimension is phase-major [n_phase][Cout] (folded up-conv), else 1
+  int tgroup;                                  // taps per weight TMA box / pipeline step (consecutive slabs)
   int halo, halo_x0, halo_y0, halo_w;
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int block_n, n_tiles, tiles_x, tiles_y, B, total_tiles, tmem_cols;
-  int Ho, Wo, Cout, wB;
+  int Ho, Wo, Cout, wB, out_cpitch;
   const float* bias;
   const float* noise;
   const float* noise_w;
   const float* res;
-  int64_t out_sb, out_sy, out_sx;
+  int64_t out_sb, out_sy, out_sx, phase_off[4];
   int act, round_tf32;
   float slope, gain, alpha, beta;
+  unsigned long long* dbg;   // optional [grid][16] cycle counters (tuning only)
 };
+
+#define VT_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
 
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs p) {
@@ -73,12 +82,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long tw[4] = {0, 0, 0, 0};
+  const long long t_begin = clock64();
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; ++s)
       for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.in_map[s][v]);
     tma_prefetch_desc(&p.w_map);
-    tma_prefetch_desc(&p.out_map);
+    for (int ph = 0; ph < p.n_phase; ++ph) tma_prefetch_desc(&p.out_map[ph]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
@@ -97,40 +108,53 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
 
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int item_w = TILE_W * p.mt;             // output columns covered by one work item
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      uint32_t a_it = 0, b_it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile / m_tiles, m = tile % m_tiles;
-        const int b = m / tiles_per_img, rem = m % tiles_per_img;
-        const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * TILE_W;
-        const int n0 = n_tile * p.block_n;
-        const int wb = p.wB > 1 ? b : 0;
-        for (int s = 0; s < p.n_src; ++s) {
-          for (int kc = 0; kc < p.kchunks[s]; ++kc) {
-            const int c0 = kc * KCH;
-            if (p.halo) {
-              const int st = a_it % p.a_stages;
-              mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 1);
+    // ================= TMA producer (whole warp converged; one elected lane issues) =================
+    // Issuing from a converged warp lets ptxas keep descriptors/coordinates in uniform registers; issuing from a
+    // `lane == 0` branch wraps every UTMALDG/UTCHMMA in an ELECT loop (measured 103 vs 59 cycles per MMA).
+    uint32_t a_it = 0, b_it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile / m_tiles, m = tile % m_tiles;
+      const int b = m / tiles_per_img, rem = m % tiles_per_img;
+      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w;
+      const int n0 = n_tile * p.block_n;
+      const int wb = p.wB > 1 ? b : 0;
+      for (int s = 0; s < p.n_src; ++s) {
+        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+          const int c0 = kc * KCH;
+          if (p.halo) {
+            const int st = a_it % p.a_stages;
+            VT_TWAIT(0, mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 1));
+            if (elect_one()) {
               mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
               tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][0], a_full(st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+            }
+            __syncwarp();
+            ++a_it;
+          }
+          for (int j = 0; j < p.n_steps; ++j) {
+            if (!p.halo) {
+              const int st = a_it % p.a_stages;
+              VT_TWAIT(0, mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 2));
+              if (elect_one()) {
+                mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
+                tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][p.step_view[j]], a_full(st), c0, ox0 + p.step_vx[j],
+                            oy0 + p.step_vy[j], b);
+              }
+              __syncwarp();
               ++a_it;
             }
-            for (int t = 0; t < p.taps; ++t) {
-              if (!p.halo) {
-                const int st = a_it % p.a_stages;
-                mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 2);
-                mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
-                tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][p.tap_view[t]], a_full(st), c0, ox0 + p.tap_vx[t],
-                            oy0 + p.tap_vy[t], b);
-                ++a_it;
-              }
+            if (j % p.tgroup == 0) {
+              // one TMA box carries the weight tiles of `tgroup` consecutive taps: (32 ch, block_n, tgroup, 1)
               const int st = b_it % p.b_stages;
-              mbar_wait(b_empty(st), ((b_it / p.b_stages) & 1) ^ 1, 3);
-              mbar_arrive_expect_tx(b_full(st), (uint32_t)(p.block_n * 128));
-              tma_load_4d(b_base + st * p.b_stage_bytes, &p.w_map, b_full(st), p.coff[s] + c0, n0, p.tap_w[t], wb);
+              VT_TWAIT(1, mbar_wait(b_empty(st), ((b_it / p.b_stages) & 1) ^ 1, 3));
+              if (elect_one()) {
+                mbar_arrive_expect_tx(b_full(st), (uint32_t)(p.block_n * 128 * p.tgroup));
+                tma_load_4d(b_base + st * p.b_stage_bytes, &p.w_map, b_full(st), p.coff[s] + c0, n0, p.step_w[j], wb);
+              }
+              __syncwarp();
               ++b_it;
             }
           }
@@ -138,139 +162,165 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      const uint32_t idesc = make_idesc_tf32(TILE_M, p.block_n);
-      uint32_t a_it = 0, b_it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int as = lt & 1;
-        mbar_wait(t_empty(as), ((lt >> 1) & 1) ^ 1, 4);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.n_src; ++s) {
-          for (int kc = 0; kc < p.kchunks[s]; ++kc) {
-            int sta = 0;
-            if (p.halo) {
+    // ================= MMA issuer (whole warp converged; one elected lane issues) =================
+    const uint32_t idesc = make_idesc_tf32(TILE_M, p.block_n);
+    uint32_t a_it = 0, b_it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int as = lt % p.acc_stages;
+      VT_TWAIT(2, mbar_wait(t_empty(as), ((lt / p.acc_stages) & 1) ^ 1, 4));
+      tc_fence_after();
+      const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * p.mt * p.block_n);
+      uint32_t first = 1;   // first K step of this work item overwrites the accumulators
+      for (int s = 0; s < p.n_src; ++s) {
+        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+          int sta = 0;
+          if (p.halo) {
+            sta = a_it % p.a_stages;
+            VT_TWAIT(0, mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 5));
+          }
+          for (int j = 0; j < p.n_steps; ++j) {
+            if (!p.halo) {
               sta = a_it % p.a_stages;
-              mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 5);
+              VT_TWAIT(0, mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 6));
             }
-            for (int t = 0; t < p.taps; ++t) {
-              if (!p.halo) {
-                sta = a_it % p.a_stages;
-                mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 6);
-              }
-              const int stb = b_it % p.b_stages;
-              mbar_wait(b_full(stb), (b_it / p.b_stages) & 1, 7);
-              tc_fence_after();
-              uint32_t a_addr = a_base + sta * p.a_stage_bytes;
-              uint32_t sbo = 1024;
-              if (p.halo) {
-                // The 128B swizzle is a function of the absolute smem address bits (TMA wrote the halo box with the
-                // same function), so a tap is just a start address shifted by whole 128-byte rows; the descriptor's
-                // base-offset field stays 0 (setting it to (addr>>7)&7 was measured WRONG on B200).
-                a_addr += (uint32_t)(((p.tap_vy[t] - p.halo_y0) * p.halo_w + (p.tap_vx[t] - p.halo_x0)) * 128);
-                sbo = (uint32_t)p.halo_w * 128u;
-              }
-              const uint64_t adesc = make_smem_desc_sw128(a_addr, sbo, 0);
-              const uint64_t bdesc = make_smem_desc_sw128(b_base + stb * p.b_stage_bytes, 1024, 0);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(b_empty(stb));
-              ++b_it;
-              if (!p.halo) { umma_commit(a_empty(sta)); ++a_it; }
+            const int stb = b_it % p.b_stages;
+            if (j % p.tgroup == 0) {
+              VT_TWAIT(1, mbar_wait(b_full(stb), (b_it / p.b_stages) & 1, 7));
             }
-            if (p.halo) { umma_commit(a_empty(sta)); ++a_it; }
+            tc_fence_after();
+            uint32_t a_addr = a_base + sta * p.a_stage_bytes;
+            uint32_t sbo = 1024;
+            if (p.halo) {
+              // The 128B swizzle is a function of the absolute smem address bits (TMA wrote the halo box with the
+              // same function), so a tap is just a start address shifted by whole 128-byte rows; the descriptor's
+              // base-offset field stays 0 (setting it to (addr>>7)&7 was measured WRONG on B200).
+              a_addr += (uint32_t)(((p.step_vy[j] - p.halo_y0) * p.halo_w + (p.step_vx[j] - p.halo_x0)) * 128);
+              sbo = (uint32_t)p.halo_w * 128u;
+            }
+            const uint64_t bdesc = make_smem_desc_sw128(
+                b_base + stb * p.b_stage_bytes + (uint32_t)((j % p.tgroup) * p.block_n * 128), 1024, 0);
+            const bool last_of_group = (j % p.tgroup == p.tgroup - 1);
+            if (elect_one()) {
+              for (int g = 0; g < p.mt; ++g) {
+                const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)(g * TILE_W * 128), sbo, 0);
+                const uint32_t d_tmem = d_tmem0 + (uint32_t)(g * p.block_n);
+                umma_tf32(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                umma_tf32(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                umma_tf32(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                umma_tf32(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+              }
+              if (last_of_group) umma_commit(b_empty(stb));
+              if (!p.halo) umma_commit(a_empty(sta));
+            }
+            __syncwarp();
+            first = 0;
+            if (last_of_group) ++b_it;
+            if (!p.halo) ++a_it;
+          }
+          if (p.halo) {
+            if (elect_one()) umma_commit(a_empty(sta));
+            __syncwarp();
+            ++a_it;
           }
         }
-        umma_commit(t_full(as));
       }
+      if (elect_one()) umma_commit(t_full(as));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int q = warp - 4;
-    const int r = q * 32 + lane;           // accumulator row == pixel index in the tile
+    const int r = q * 32 + lane;           // accumulator row == pixel index in the M tile
     const int ty = r / TILE_W, tx = r % TILE_W;
     const bool store_thread = (threadIdx.x == 128);
     const float nw = (p.noise && p.noise_w) ? *p.noise_w : 0.f;
     uint32_t lt = 0, chunk = 0;
+    const int nchunks = p.block_n / 32;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
-      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * TILE_W;
+      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w;
       const int n0 = n_tile * p.block_n;
-      const int oy = oy0 + ty, ox = ox0 + tx;
-      const bool in_img = oy < p.Ho && ox < p.Wo;
-      const int64_t off = (int64_t)b * p.out_sb + (int64_t)oy * p.out_sy + (int64_t)ox * p.out_sx;
-      const float nz = (p.noise && in_img) ? nw * p.noise[((int64_t)b * p.Ho + oy) * p.Wo + ox] : 0.f;
-      const int as = lt & 1;
-      mbar_wait(t_full(as), (lt >> 1) & 1, 8);
+      const int as = lt % p.acc_stages;
+      VT_TWAIT(0, mbar_wait(t_full(as), (lt / p.acc_stages) & 1, 8));
       tc_fence_after();
-      const int nchunks = p.block_n / 32;
-      for (int j = 0; j < nchunks; ++j, ++chunk) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + j * 32), v);
-        if (j == nchunks - 1) {
-          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty(as));
-        }
-        const int nb = n0 + j * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = v[i];
-          if (p.noise) x += nz;
-          if (p.bias) x += __ldg(p.bias + nb + i);
-          if (p.act == VT_ACT_LRELU) x = vt_lrelu(x, p.slope) * p.gain;
-          else if (p.act == VT_ACT_RELU_TANH) x = tanhf(fmaxf(x, 0.f));
-          v[i] = x;
-        }
-        if (p.res) {
-          if (in_img) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res + off + nb);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 rv = __ldg(rp + i);
-              v[4 * i + 0] = v[4 * i + 0] * p.alpha + p.beta * rv.x;
-              v[4 * i + 1] = v[4 * i + 1] * p.alpha + p.beta * rv.y;
-              v[4 * i + 2] = v[4 * i + 2] * p.alpha + p.beta * rv.z;
-              v[4 * i + 3] = v[4 * i + 3] * p.alpha + p.beta * rv.w;
-            }
+      for (int g = 0; g < p.mt; ++g) {
+        const int oy = oy0 + ty, ox = ox0 + g * TILE_W + tx;
+        const bool in_img = oy < p.Ho && ox < p.Wo;
+        const int64_t off0 = (int64_t)b * p.out_sb + (int64_t)oy * p.out_sy + (int64_t)ox * p.out_sx;
+        for (int j = 0; j < nchunks; ++j, ++chunk) {
+          // column -> (phase, channel): the N dimension is phase-major [n_phase][Cout]; a 32-column chunk never straddles
+          const int ncol = n0 + j * 32;
+          const int ph = ncol / p.Cout;
+          const int nb = ncol - ph * p.Cout;
+          const int64_t off = p.phase_off[ph] + off0;
+          const float nz = (p.noise && in_img) ? nw * p.noise[off / p.out_cpitch] : 0.f;
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.block_n + j * 32), v);
+          if (g == p.mt - 1 && j == nchunks - 1) {
+            // every accumulator of this stage is in registers: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty(as));
           }
-        } else if (p.alpha != 1.f) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-        }
-        if (p.round_tf32) {
+          for (int i = 0; i < 32; ++i) {
+            float x = v[i];
+            if (p.noise) x += nz;
+            if (p.bias) x += __ldg(p.bias + nb + i);
+            if (p.act == VT_ACT_LRELU) x = vt_lrelu(x, p.slope) * p.gain;
+            else if (p.act == VT_ACT_RELU_TANH) x = tanhf(fmaxf(x, 0.f));
+            v[i] = x;
+          }
+          if (p.res) {
+            if (in_img) {
+              const float4* rp = reinterpret_cast<const float4*>(p.res + off + nb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = vt_round_tf32(v[i]);
-        }
-        const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
-        if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
-        named_bar_sync(1, 128);
-        const uint32_t row = sbuf + (uint32_t)r * 128u;
+              for (int i = 0; i < 8; ++i) {
+                const float4 rv = __ldg(rp + i);
+                v[4 * i + 0] = v[4 * i + 0] * p.alpha + p.beta * rv.x;
+                v[4 * i + 1] = v[4 * i + 1] * p.alpha + p.beta * rv.y;
+                v[4 * i + 2] = v[4 * i + 2] * p.alpha + p.beta * rv.z;
+                v[4 * i + 3] = v[4 * i + 3] * p.alpha + p.beta * rv.w;
+              }
+            }
+          } else if (p.alpha != 1.f) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t dst = row + (uint32_t)((c ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * c]), "f"(v[4 * c + 1]),
-                       "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (store_thread) {
-          tma_store_4d(&p.out_map, sbuf, nb, ox0, oy0, b);
-          tma_store_commit();
+            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+          }
+          if (p.round_tf32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = vt_round_tf32(v[i]);
+          }
+          const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
+          if (store_thread) VT_TWAIT(1, tma_store_wait_read<1>());   // the store that used this buffer two chunks ago has read it
+          VT_TWAIT(2, named_bar_sync(1, 128));
+          const uint32_t row = sbuf + (uint32_t)r * 128u;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t dst = row + (uint32_t)((c ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                         "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (store_thread) {
+            tma_store_4d(&p.out_map[ph], sbuf, nb, ox0 + g * TILE_W, oy0, b);
+            tma_store_commit();
+          }
         }
       }
     }
     if (store_thread) tma_store_wait_all<0>();
   }
 
+  if (p.dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+    const int role = warp == 4 ? 2 : warp;   // 0 producer, 1 mma, 2 epilogue
+    unsigned long long* o = p.dbg + (size_t)blockIdx.x * 16 + role * 5;
+    o[0] = (unsigned long long)(clock64() - t_begin);
+    o[1] = (unsigned long long)tw[0]; o[2] = (unsigned long long)tw[1]; o[3] = (unsigned long long)tw[2]; o[4] = (unsigned long long)tw[3];
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -317,6 +367,9 @@ int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
 }
 
 int g_tc_mode = 1;  // 0: one TMA box per tap; 1: one halo box per K chunk + row-shifted descriptors
+int g_tc_mt = 0;    // 0: automatic M-tiles per work item; 1/2/4: forced
+unsigned long long* g_tc_dbg = nullptr;   // device buffer [148][16] set through vt_set_debug_buffer (tuning only)
+int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
 #define VT_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)
@@ -326,6 +379,8 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
     VT_SUP(d->src_cstride[s] % 4 == 0, "conv_tc: channel stride must be a multiple of 4");
   }
   VT_SUP(d->stride == 1 || d->stride == 2, "conv_tc: stride must be 1 or 2");
+  VT_SUP(d->n_phase == 1 || (d->n_phase == 4 && d->stride == 1 && g_tc_mode != 0 && !d->res), "conv_tc: phases need stride 1, halo mode, no residual");
+  for (int ph = 0; ph < d->n_phase; ++ph) VT_SUP(d->phase_off[ph] % 4 == 0, "conv_tc: phase offset must be a multiple of 4 floats");
   VT_SUP(d->out_sx % 4 == 0 && d->out_sy % 4 == 0 && d->out_sb % 4 == 0, "conv_tc: output strides must be multiples of 4 floats");
   VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
@@ -338,8 +393,12 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
 
 extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
+  if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
+  if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
   return -1;
 }
+
+extern "C" int vt_set_debug_buffer(void* p) { g_tc_dbg = (unsigned long long*)p; return 0; }
 
 extern "C" int vt_conv2d_tc_supported(const vt_conv_desc* d) {
   if (!d || d->struct_size != (int)sizeof(vt_conv_desc)) return 0;
@@ -352,70 +411,103 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
 
   static thread_local TcArgs a;  // large (tensor maps); reused to avoid stack churn
   memset(&a, 0, sizeof(a));
-  // ---- output tile / N tile
-  int bn = 256;
-  while (bn > 32 && (d->Cout % bn) != 0) bn -= 32;
-  VT_CHECK(d->Cout % bn == 0, "conv_tc: no N tile for Cout=%d", d->Cout);
-  a.block_n = bn;
-  a.n_tiles = d->Cout / bn;
-  a.tiles_x = (int)vt_cdiv(d->Wo, TILE_W);
-  a.tiles_y = (int)vt_cdiv(d->Ho, TILE_H);
-  a.B = d->B;
-  const int64_t total = (int64_t)a.n_tiles * a.B * a.tiles_x * a.tiles_y;
-  VT_CHECK(total < (1LL << 31), "conv_tc: too many tiles");
-  a.total_tiles = (int)total;
-  int tc = 32;
-  while (tc < 2 * bn) tc *= 2;
-  a.tmem_cols = tc;
-  a.Ho = d->Ho; a.Wo = d->Wo; a.Cout = d->Cout; a.wB = d->wB;
+  a.n_phase = d->n_phase;
+  a.Ho = d->Ho; a.Wo = d->Wo; a.Cout = d->Cout; a.wB = d->wB; a.out_cpitch = d->out_cpitch;
   a.bias = d->bias; a.noise = d->noise; a.noise_w = d->noise_w; a.res = d->res;
   a.out_sb = d->out_sb; a.out_sy = d->out_sy; a.out_sx = d->out_sx;
+  for (int ph = 0; ph < 4; ++ph) a.phase_off[ph] = d->phase_off[ph < d->n_phase ? ph : 0];
+  a.dbg = g_tc_dbg;
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
+  a.B = d->B;
 
   // ---- K iteration space
   a.n_src = d->n_src;
   int coff = 0;
   for (int s = 0; s < d->n_src; ++s) { a.kchunks[s] = d->src_c[s] / KCH; a.coff[s] = coff; coff += d->src_c[s]; }
-  a.taps = d->taps;
+  a.n_steps = d->taps;
   int dxmin = 1 << 30, dxmax = -(1 << 30), dymin = 1 << 30, dymax = -(1 << 30);
   for (int t = 0; t < d->taps; ++t) {
-    a.tap_w[t] = d->tap_w[t];
-    if (d->stride == 1) {
-      a.tap_view[t] = 0; a.tap_vx[t] = d->tap_dx[t]; a.tap_vy[t] = d->tap_dy[t];
-    } else {
+    int view = 0, vx = d->tap_dx[t], vy = d->tap_dy[t];
+    if (d->stride == 2) {
       const int px = d->tap_dx[t] & 1, py = d->tap_dy[t] & 1;
-      a.tap_view[t] = py * 2 + px;
-      a.tap_vx[t] = (d->tap_dx[t] - px) / 2;
-      a.tap_vy[t] = (d->tap_dy[t] - py) / 2;
+      view = py * 2 + px;
+      vx = (d->tap_dx[t] - px) / 2;
+      vy = (d->tap_dy[t] - py) / 2;
     }
-    dxmin = a.tap_vx[t] < dxmin ? a.tap_vx[t] : dxmin; dxmax = a.tap_vx[t] > dxmax ? a.tap_vx[t] : dxmax;
-    dymin = a.tap_vy[t] < dymin ? a.tap_vy[t] : dymin; dymax = a.tap_vy[t] > dymax ? a.tap_vy[t] : dymax;
+    VT_CHECK(vx >= -100 && vx <= 100 && vy >= -100 && vy <= 100, "conv_tc: tap offset out of range");
+    a.step_view[t] = (int8_t)view; a.step_vx[t] = (int8_t)vx; a.step_vy[t] = (int8_t)vy;
+    a.step_w[t] = (int16_t)d->tap_w[t];
+    dxmin = vx < dxmin ? vx : dxmin; dxmax = vx > dxmax ? vx : dxmax;
+    dymin = vy < dymin ? vy : dymin; dymax = vy > dymax ? vy : dymax;
   }
-  // ---- operand staging plan
-  const int halo_w = TILE_W + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
-  const int halo_bytes = halo_w * halo_h * 128;
-  a.halo = (g_tc_mode != 0) && d->stride == 1 && d->taps > 1 && halo_w <= 256 && halo_h <= 256 &&
-           halo_bytes <= d->taps * TILE_M * 128 / 2 && halo_bytes <= 64 * 1024;
-  a.halo_x0 = dxmin; a.halo_y0 = dymin; a.halo_w = halo_w;
-  a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
-  a.a_stage_bytes = (int)(vt_cdiv(a.a_tx_bytes, 1024) * 1024);
-  a.b_stage_bytes = bn * 128;
+
+  // ---- N tile and accumulator plan (TMEM: 512 columns)
+  // GEMM N = n_phase * Cout (phase-major rows of the weight tensor); N tile = largest multiple of 32 <= 256 dividing it
+  const int n_eff = d->n_phase * d->Cout;
+  int bn = 256;
+  while (bn > 32 && (n_eff % bn) != 0) bn -= 32;
+  VT_CHECK(n_eff % bn == 0, "conv_tc: no N tile for N=%d", n_eff);
+  const bool can_halo = (g_tc_mode != 0) && d->stride == 1 && d->taps > 1;
+  // M tiles per work item: share each weight tile across `mt` pixel tiles when N is small (weights dominate L2->smem
+  // traffic there); bounded by TMEM columns and by the halo box fitting a pipeline stage.
+  int mt = 1;
+  if (can_halo && g_tc_mt != 1) {
+    int want = (g_tc_mt > 0) ? g_tc_mt : (bn >= 256 ? 1 : (bn >= 128 ? 2 : 4));
+    // keep two accumulator stages (epilogue/mainloop overlap) unless forced: 2 * n_phase * mt * bn <= 512 TMEM columns
+    const int col_budget = (g_tc_mt > 0) ? 512 : ((2 * bn <= 512) ? 256 : 512);
+    while (want > 1 && (want * bn > col_budget || d->Wo <= TILE_W * (want / 2))) want /= 2;
+    mt = want;
+  }
   const int fixed = 2 * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
-  a.a_stages = a.halo ? 2 : 4;
-  a.b_stages = 4;
-  while (a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed > MAX_SMEM) {
-    if (a.b_stages > 2 && a.b_stages * a.b_stage_bytes >= a.a_stages * a.a_stage_bytes) --a.b_stages;
-    else if (a.a_stages > 2) --a.a_stages;
-    else if (a.b_stages > 2) --a.b_stages;
-    else break;
+  int smem_bytes = 0;
+  // taps per weight box: as many consecutive slabs as fit ~36 KB, dividing the step count, never crossing a phase
+  int tgroup = 1;
+  if (g_tc_tgroup != 1) {
+    for (int tg = d->taps; tg >= 2; --tg) {
+      if (d->taps % tg != 0 || tg * bn * 128 > (g_tc_tgroup > 1 ? g_tc_tgroup : 36) * 1024) continue;
+      bool ok = true;
+      for (int t = 0; t < d->taps && ok; ++t)
+        if (t % tg != 0 && d->tap_w[t] != d->tap_w[t - 1] + 1) ok = false;
+      if (ok) { tgroup = tg; break; }
+    }
   }
-  if (a.halo && a.a_stages < 3 && (a.a_stages + 1) * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed <= MAX_SMEM) ++a.a_stages;
-  while (a.b_stages < 8 && a.a_stages * a.a_stage_bytes + (a.b_stages + 1) * a.b_stage_bytes + fixed <= MAX_SMEM &&
-         a.b_stages < 6)
-    ++a.b_stages;
-  const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed;
+  a.tgroup = tgroup;
+  for (;; mt /= 2) {
+    const int halo_w = TILE_W * mt + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
+    const int halo_bytes = halo_w * halo_h * 128;
+    a.halo = can_halo && halo_w <= 256 && halo_h <= 256 && halo_bytes <= 96 * 1024 &&
+             (mt > 1 || halo_bytes <= d->taps * TILE_M * 128 / 2);
+    if (!a.halo && mt > 1) continue;
+    a.halo_x0 = dxmin; a.halo_y0 = dymin; a.halo_w = halo_w;
+    a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
+    // shared memory plan: A ring (halo boxes or per-tap tiles) + B ring (weight tiles) + 2 output staging buffers
+    a.a_stage_bytes = (int)(vt_cdiv(a.a_tx_bytes, 1024) * 1024);
+    a.b_stage_bytes = bn * 128 * tgroup;
+    a.a_stages = a.halo ? 3 : 4;
+    a.b_stages = tgroup > 1 ? 4 : 6;
+    while (a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed > MAX_SMEM) {
+      if (a.b_stages > 3) --a.b_stages;
+      else if (a.a_stages > 2) --a.a_stages;
+      else if (a.b_stages > 2) --a.b_stages;
+      else break;
+    }
+    smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed;
+    if (smem_bytes <= MAX_SMEM || mt == 1) break;
+  }
   VT_CHECK(smem_bytes <= MAX_SMEM && a.a_stages >= 2 && a.b_stages >= 2 && a.a_stages <= 8 && a.b_stages <= 8,
-           "conv_tc: shared memory plan does not fit (%d B)", smem_bytes);
+           "conv_tc: shared memory plan does not fit (%d B, mt=%d, bn=%d)", smem_bytes, mt, bn);
+  a.mt = mt;
+  a.acc_stages = (2 * mt * bn <= 512) ? 2 : 1;
+  int tc = 32;
+  while (tc < a.acc_stages * mt * bn) tc *= 2;
+  a.tmem_cols = tc;
+  a.block_n = bn;
+  a.n_tiles = n_eff / bn;
+  a.tiles_x = (int)vt_cdiv(d->Wo, TILE_W * mt);
+  a.tiles_y = (int)vt_cdiv(d->Ho, TILE_H);
+  const int64_t total = (int64_t)a.n_tiles * a.B * a.tiles_x * a.tiles_y;
+  VT_CHECK(total < (1LL << 31), "conv_tc: too many tiles");
+  a.total_tiles = (int)total;
 
   // ---- tensor maps
   for (int s = 0; s < d->n_src; ++s) {
@@ -423,36 +515,40 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     if (d->stride == 1) {
       const uint64_t dims[4] = {cs, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
       const uint64_t str[3] = {cs * 4, (uint64_t)d->W * cs * 4, (uint64_t)d->H * d->W * cs * 4};
-      const uint32_t box[4] = {KCH, (uint32_t)(a.halo ? halo_w : TILE_W), (uint32_t)(a.halo ? halo_h : TILE_H), 1};
+      const uint32_t box[4] = {KCH, (uint32_t)(a.halo ? a.halo_w : TILE_W),
+                               (uint32_t)(a.halo ? TILE_H + (dymax - dymin) : TILE_H), 1};
       if (make_map4(&a.in_map[s][0], d->src[s], dims, str, box, "input")) return 1;
       for (int v = 1; v < 4; ++v) a.in_map[s][v] = a.in_map[s][0];
     } else {
       // parity views: view (py,px)[vy][vx] = in[2*vy+py][2*vx+px]
+      bool have0 = false;
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
           const int vw = (d->W - px + 1) / 2, vh = (d->H - py + 1) / 2;
           CUtensorMap* mp = &a.in_map[s][py * 2 + px];
-          if (vw < 1 || vh < 1) { *mp = a.in_map[s][0]; continue; }
+          if (vw < 1 || vh < 1) { if (have0) *mp = a.in_map[s][0]; continue; }
           const uint64_t dims[4] = {cs, (uint64_t)vw, (uint64_t)vh, (uint64_t)d->B};
           const uint64_t str[3] = {2 * cs * 4, 2 * (uint64_t)d->W * cs * 4, (uint64_t)d->H * d->W * cs * 4};
           const uint32_t box[4] = {KCH, TILE_W, TILE_H, 1};
           if (make_map4(mp, d->src[s] + ((int64_t)py * d->W + px) * cs, dims, str, box, "input(parity)")) return 1;
+          have0 = true;
         }
     }
   }
   {
     const uint64_t wc = (uint64_t)d->w_cstride;
-    const uint64_t dims[4] = {wc, (uint64_t)d->Cout, (uint64_t)d->w_taps, (uint64_t)d->wB};
-    const uint64_t str[3] = {wc * 4, (uint64_t)d->Cout * wc * 4, (uint64_t)d->w_taps * d->Cout * wc * 4};
-    const uint32_t box[4] = {KCH, (uint32_t)bn, 1, 1};
+    const uint64_t dims[4] = {wc, (uint64_t)n_eff, (uint64_t)d->w_taps, (uint64_t)d->wB};
+    const uint64_t str[3] = {wc * 4, (uint64_t)n_eff * wc * 4, (uint64_t)d->w_taps * n_eff * wc * 4};
+    const uint32_t box[4] = {KCH, (uint32_t)bn, (uint32_t)a.tgroup, 1};
     if (make_map4(&a.w_map, d->weight, dims, str, box, "weight")) return 1;
   }
-  {
+  for (int ph = 0; ph < d->n_phase; ++ph) {
     const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
-    const uint64_t str[3] = {(uint64_t)d->out_sx * 4, (uint64_t)d->out_sy * 4, (uint64_t)(d->B > 1 ? d->out_sb : d->out_sy * d->Ho) * 4};
+    const uint64_t str[3] = {(uint64_t)d->out_sx * 4, (uint64_t)d->out_sy * 4, (uint64_t)d->out_sb * 4};
     const uint32_t box[4] = {32, TILE_W, TILE_H, 1};
-    if (make_map4(&a.out_map, d->out, dims, str, box, "output")) return 1;
+    if (make_map4(&a.out_map[ph], d->out + d->phase_off[ph], dims, str, box, "output")) return 1;
   }
+  for (int ph = d->n_phase; ph < 4; ++ph) a.out_map[ph] = a.out_map[0];
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -467,6 +563,68 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   return 0;
 }
 
-extern "C" int vt_selftest_tc_gemm(const float*, const float*, float*, int, int, int, int, void*) {
-  return vt_set_error("selftest_tc_gemm: use vt_conv2d_tc_tf32 with a 1x1 tap (tests/test_conv_tc.py)");
+// ---- tcgen05 issue-rate microbenchmark (tuning aid, tests/ and tools/ only) -----------------------------------------
+// One CTA per SM issues `reps` x 4 MMAs (M=128, N, K=8) on zero-filled smem operands without any TMA traffic.
+// variant bit 0: alternate between two accumulators; bit 1: issue from a converged warp (elect.sync) instead of a
+// lane-0 branch; bit 2: commit + wait after every group of 4 MMAs (round-trip latency).
+__global__ void __launch_bounds__(128, 1)
+tc_issue_bench_kernel(float* out, int N, int reps, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_addr = base, b_addr = base + 16384, bar = base + 16384 + 32768, slot = bar + 16;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(gen)[i] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  if (warp == 1) { tmem_alloc(slot, 512); tc_fence_before(); }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
+  long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint64_t adesc = make_smem_desc_sw128(a_addr, 1024, 0), bdesc = make_smem_desc_sw128(b_addr, 1024, 0);
+    uint32_t phase = 0;
+    const bool converged = variant & 2;
+    if (converged || lane == 0) {
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        const uint32_t d = tmem + ((variant & 1) ? (uint32_t)((r & 1) * N) : 0u);
+        if (converged) {
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+          }
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+        }
+        if (variant & 4) {
+          if (!converged || elect_one()) umma_commit(bar);
+          mbar_wait(bar, phase, 99);
+          phase ^= 1;
+        }
+      }
+      if (!(variant & 4)) {
+        if (!converged || elect_one()) umma_commit(bar);
+        mbar_wait(bar, phase, 98);
+      }
+      t1 = clock64();
+    }
+    if (lane == 0 && blockIdx.x == 0) { out[0] = (float)(t1 - t0) / (float)(reps * 4); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+extern "C" int vt_selftest_tc_gemm(const float*, const float*, float* D, int, int N, int K, int variant, void* stream) {
+  VT_CHECK(D && N >= 16 && N <= 256 && N % 16 == 0 && K >= 1, "selftest_tc_gemm: D (device float[1]) / N / reps invalid");
+  const int smem = 16384 + 32768 + 1024 + 1024;
+  VT_CUDA(cudaFuncSetAttribute(tc_issue_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_issue_bench_kernel<<<vt_num_sms(), 128, smem, (cudaStream_t)stream>>>(D, N, K, variant);
+  VT_LAUNCH_CHECK();
+  return 0;
 }

@@ -94,7 +94,61 @@ modulate_weights_kernel(const float* __restrict__ W, const float* __restrict__ s
   }
 }
 
+// Fold Blur o conv_transpose2d(stride 2) into 4 phase kernels: one thread per (b, n, c) reads the 9 modulated weights and
+// writes the 36 folded ones.  blur: out[o] = sum_k kf[k] * T[o + k - 1], kf = flipped 4-tap kernel; T[2i + kap] += x[i] w[kap]
+//   => G_r[dlt] = sum_kap w[kap] * kf[2*dlt + kap - r + 1]   (r = output parity, dlt = input offset in {-1,0,1}), per axis.
+__global__ void __launch_bounds__(256)
+fold_upconv_kernel(const float* __restrict__ w, const float* __restrict__ blur, float* __restrict__ out, int wB, int Cout,
+                   int cpad, int round_tf32) {
+  __shared__ float kf[4][4];
+  if (threadIdx.x < 16) kf[threadIdx.x / 4][threadIdx.x % 4] = blur[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)];
+  __syncthreads();
+  const int64_t per_b = (int64_t)Cout * cpad;
+  const int64_t total = (int64_t)wB * per_b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_b, nc = i % per_b;
+    float wv[3][3];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wv[t / 3][t % 3] = w[(b * 9 + t) * per_b + nc];
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < 2; ++rx)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            float g = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int iy = 2 * dy + ky - ry + 1;
+              if (iy < 0 || iy > 3) continue;
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * dx + kx - rx + 1;
+                if (ix < 0 || ix > 3) continue;
+                g = fmaf(wv[ky][kx], kf[iy][ix], g);
+              }
+            }
+            // out layout [wB][9 taps][4 phases][Cout][cpad]: the 4 phases are stacked along the GEMM N dimension
+            const int slab = (dy + 1) * 3 + (dx + 1), ph = ry * 2 + rx;
+            out[((b * 9 + slab) * 4 + ph) * per_b + nc] = round_tf32 ? vt_round_tf32(g) : g;
+          }
+  }
+}
+
 }  // namespace
+
+extern "C" int vt_fold_upconv_weights_f32(const float* w, const float* blur, float* out, int wB, int Cout, int cpad,
+                                          int round_tf32, void* stream) {
+  VT_CHECK(w && blur && out && wB >= 1 && Cout >= 1 && cpad >= 1, "fold_upconv_weights: bad args");
+  const int64_t total = (int64_t)wB * Cout * cpad;
+  int64_t blocks = vt_cdiv(total, 256);
+  if (blocks > (int64_t)vt_num_sms() * 8) blocks = (int64_t)vt_num_sms() * 8;
+  fold_upconv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, blur, out, wB, Cout, cpad, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int vt_linear_f32(const float* in, const float* weight, const float* bias, float* out, int rows, int in_dim,
                              int out_dim, float w_scale, float b_scale, int act, void* stream) {

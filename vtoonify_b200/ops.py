@@ -31,6 +31,20 @@ def get_precision() -> str:
     return _precision
 
 
+# algorithm switches (kept so tests can compare both formulations on the GPU)
+_options = {"fold_upconv": True}
+
+
+def set_option(name: str, value) -> None:
+    if name not in _options:
+        raise KeyError(name)
+    _options[name] = value
+
+
+def get_option(name: str):
+    return _options[name]
+
+
 # Optional per-launch timing of the tensor-core convolution (bench.py's roofline leg): when set to a list, every
 # vt_conv2d_tc_tf32 launch appends (start_event, end_event, algorithmic_flops, algorithmic_bytes, label).
 _tc_profile = None
@@ -201,7 +215,7 @@ def conv_taps(k: int, padding: int, dilation: int = 1):
 
 def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride: int, Ho: int, Wo: int,
                 out: Optional[torch.Tensor] = None, out_view: Optional[Tuple[int, int, int, int]] = None,
-                src_c: Optional[Sequence[int]] = None,
+                src_c: Optional[Sequence[int]] = None, phase_offs: Optional[Sequence[int]] = None,
                 bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                 noise_w: Optional[torch.Tensor] = None, act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0,
                 res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
@@ -210,10 +224,14 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
 
     ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
     ``out_view``: (offset_elems, sb, sy, sx) strided view into ``out`` (used for polyphase transposed conv).
+    ``phase_offs``: 4 element offsets -> one launch computes 4 output phases: ``weight`` rows are phase-major
+    ``[n_phase * Cout]`` per tap and phase ``ph`` is stored through the strided view ``out_view`` shifted by ``phase_offs[ph]``.
     """
     prec = precision or _precision
     B, H, W, _ = srcs[0].shape
     wB, w_taps, Cout, w_cs = weight.shape
+    if phase_offs is not None:
+        Cout //= len(phase_offs)          # weight rows are phase-major [n_phase * Cout]
     _req_cuda(weight, bias, noise, noise_w, res, *srcs)
     d = ConvDesc()
     d.struct_size = _lib.ctypes.sizeof(ConvDesc)
@@ -227,8 +245,9 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     d.B, d.H, d.W, d.Ho, d.Wo = B, H, W, Ho, Wo
     d.stride = stride
     d.taps = len(taps)
-    for t, (dy, dx, tw) in enumerate(taps):
-        d.tap_dy[t], d.tap_dx[t], d.tap_w[t] = dy, dx, tw
+    for t, tap in enumerate(taps):
+        d.tap_dy[t], d.tap_dx[t], d.tap_w[t] = tap[0], tap[1], tap[2]
+    d.n_phase = 1 if phase_offs is None else len(phase_offs)
     d.weight = weight.data_ptr()
     d.wB, d.w_taps, d.w_cstride, d.Cout = wB, w_taps, w_cs, Cout
     if out is None:
@@ -239,7 +258,13 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
             raise _lib.VtError("conv2d_nhwc: bad out tensor")
     else:
         off, sb, sy, sx = out_view
-    d.out = out.data_ptr() + 4 * off
+    d.out = out.data_ptr()
+    d.out_cpitch = out.shape[-1]
+    if phase_offs is None:
+        d.phase_off[0] = off
+    else:
+        for i, po in enumerate(phase_offs):
+            d.phase_off[i] = off + po
     d.out_sb, d.out_sy, d.out_sx = sb, sy, sx
     d.bias = _ptr(bias)
     d.noise = _ptr(noise)
@@ -256,12 +281,12 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
         if _tc_profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             cin = sum(int(d.src_c[i]) for i in range(d.n_src))
-            flops = 2.0 * B * Ho * Wo * Cout * cin * len(taps)
-            nbytes = 4.0 * (B * H * W * cin + B * Ho * Wo * Cout + weight.numel())
+            flops = 2.0 * B * Ho * Wo * Cout * cin * len(taps)   # algorithmic (the folded up-conv issues 4x this)
+            nbytes = 4.0 * (B * H * W * cin + B * Ho * Wo * Cout * d.n_phase + weight.numel())
             e0.record()
             check(lib.vt_conv2d_tc_tf32(d, _stream()))
             e1.record()
-            _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout} k{len(taps)} s{stride} {H}x{W}"))
+            _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout}{'x4up' if d.n_phase > 1 else ''} k{len(taps)} s{stride} {H}x{W}"))
         else:
             check(lib.vt_conv2d_tc_tf32(d, _stream()))
     else:
@@ -291,6 +316,38 @@ def conv_transpose2d_s2_k3_nhwc(x: torch.Tensor, weight: torch.Tensor, precision
             Wo = W + 1 if px == 0 else W
             view = ((py * Wf + px) * Cout, Hf * Wf * Cout, 2 * Wf * Cout, 2 * Cout)
             conv2d_nhwc([x], weight, taps, 1, Ho, Wo, out=out, out_view=view, precision=precision)
+    return out
+
+
+def fold_upconv_weights(w: torch.Tensor, blur_kernel: torch.Tensor) -> torch.Tensor:
+    """[wB, 9, Cout, cpad] modulated weights (un-rounded) + 4x4 blur -> [wB, 9, 4*Cout, cpad]: per tap the 4 phase kernels
+    stacked along the GEMM N dimension."""
+    _req_cuda(w, blur_kernel)
+    wB, nine, Cout, cpad = w.shape
+    if nine != 9 or tuple(blur_kernel.shape) != (4, 4):
+        raise _lib.VtError("fold_upconv_weights: needs 3x3 weights and a 4x4 blur kernel")
+    out = torch.empty((wB, 9, 4 * Cout, cpad), device=w.device, dtype=torch.float32)
+    check(_lib.load().vt_fold_upconv_weights_f32(w.data_ptr(), blur_kernel.contiguous().data_ptr(), out.data_ptr(), wB, Cout,
+                                                 cpad, _round_flag(), _stream()))
+    return out
+
+
+_UP2_TAPS = [(dy, dx, (dy + 1) * 3 + (dx + 1)) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+def conv_up2_folded_nhwc(x: torch.Tensor, w_folded: torch.Tensor, bias=None, noise=None, noise_w=None, act: int = ACT_NONE,
+                         slope: float = 0.2, gain: float = 1.0, precision: Optional[str] = None) -> torch.Tensor:
+    """Blur(conv_transpose2d(x, w, stride 2)) as ONE 3x3 convolution with N = 4*Cout (the 4 output phases stacked along
+    the GEMM N dimension); the (2H+1)x(2W+1) intermediate of model/stylegan/model.py:281-285 never exists.
+    Output [B, 2H, 2W, Cout] with the StyledConv tail (noise, bias, leaky relu) in the epilogue."""
+    B, H, W, _ = x.shape
+    Cout = w_folded.shape[2] // 4
+    Hf, Wf = 2 * H, 2 * W
+    out = torch.empty((B, Hf, Wf, Cout), device=x.device, dtype=torch.float32)
+    view = (0, Hf * Wf * Cout, 2 * Wf * Cout, 2 * Cout)
+    offs = [(ry * Wf + rx) * Cout for ry in (0, 1) for rx in (0, 1)]
+    conv2d_nhwc([x], w_folded, _UP2_TAPS, 1, H, W, out=out, out_view=view, phase_offs=offs, bias=bias, noise=noise,
+                noise_w=noise_w, act=act, slope=slope, gain=gain, precision=precision)
     return out
 
 

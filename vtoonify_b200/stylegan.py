@@ -198,14 +198,20 @@ class ModulatedConv2d(nn.Module):
         """x NHWC -> NHWC.  Optional fused StyledConv epilogue (noise, bias, leaky relu)."""
         B, H, W, Cs = x.shape
         k = self.kernel_size
-        w = self.modulated_weights(style, Cs, externalweight)
         a = ACT_LRELU if act else ACT_NONE
         if self.upsample:
             if k != 3:
                 raise NotImplementedError("upsampling ModulatedConv2d is 3x3 in StyleGAN2")
+            if tuple(self.blur.kernel.shape) == (4, 4) and tuple(self.blur.pad) == (1, 1) and ops.get_option("fold_upconv"):
+                # Blur o conv_transpose folded into 4 phase-specific 3x3 kernels: one launch, no intermediate tensor
+                w9 = self.modulated_weights(style, Cs, externalweight, round_tf32=False)
+                wf = ops.fold_upconv_weights(w9, self.blur.kernel)
+                return ops.conv_up2_folded_nhwc(x, wf, bias=bias, noise=noise, noise_w=noise_w, act=a, slope=slope, gain=gain)
+            w = self.modulated_weights(style, Cs, externalweight)
             t = ops.conv_transpose2d_s2_k3_nhwc(x, w)
             return ops.fir_nhwc(t, self.blur.kernel, self.blur.pad, bias=bias, noise=noise, noise_w=noise_w, act=act,
                                 slope=slope, gain=gain)
+        w = self.modulated_weights(style, Cs, externalweight)
         if self.downsample:
             xb = ops.fir_nhwc(x, self.blur.kernel, self.blur.pad)
             Ho = ops.conv_out_size(xb.shape[1], k, 2, 0, 1)

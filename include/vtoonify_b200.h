@@ -150,8 +150,8 @@ typedef struct vt_smalln_desc {
   const float* planar_weight;   /* [w_taps][Cout][n_planar] weights of the planar channels       */
   const float* src;             /* NHWC [B,H,W,src_cstride] (may be NULL if src_c == 0)          */
   int32_t src_c, src_cstride;
-  const float* src2;            /* optional second NHWC source combined as |src - src2| or src*mul */
-  int32_t src2_mode;            /* 0 none                                                        */
+  const float* src2;            /* optional second NHWC source (same shape as src)                */
+  int32_t src2_mode;            /* 0 none; 1: input = virtual concat [src | abs(src - src2)], weight rows hold 2*src_c */
   int32_t B, H, W;
   int32_t taps;
   int32_t tap_dy[VT_MAX_TAPS], tap_dx[VT_MAX_TAPS], tap_w[VT_MAX_TAPS];
@@ -165,8 +165,14 @@ typedef struct vt_smalln_desc {
   float* mul_out;               /* optional NHWC [B,H,W,mul_c]: mul_src * out[:,0] (f_E * m_E)   */
   const float* mul_src;
   int32_t mul_c, round_tf32;
+  const float* tap_const;       /* optional [wB][w_taps][Cout]: constant added per in-bounds tap (folded affine) */
 } vt_smalln_desc;
 int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream);
+/* Fold a per-(b,c) affine (AdaIN: gamma*(x-mean)*rstd+beta, model/dualstylegan.py:16-21) into conv weights:
+ * w: [taps_n][C2] (rows = tap*N+n), stats: [B][C2][2] (mean, rstd), gamma_beta: [B][2*C2] ->
+ * out_w: [B][taps_n][C2] = w*gamma*rstd, out_k: [B][taps_n] = sum_c w*(beta - gamma*mean*rstd). */
+int vt_affine_fold_weights_f32(const float* w, const float* stats, const float* gamma_beta, float* out_w, float* out_k,
+                               int B, int taps_n, int C2, void* stream);
 
 /* ---- FIR on NHWC (Blur after transposed conv) with fused noise + bias + leaky relu -------- */
 /* in : [B, H, W, C] ; kernel [kh,kw] (device, flipped like upfirdn2d); pad (p0,p1) both axes.

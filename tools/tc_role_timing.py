@@ -22,9 +22,9 @@ def report(name, fn, flops):
     ms = e0.elapsed_time(e1)
     tot = d[:, 0].mean().item()
     def pct(i): return 100 * d[:, i].mean().item() / max(tot, 1)
-    print(f"{name:34s} {ms:7.3f} ms {flops / ms / 1e9:6.0f} TF/s | cycles/CTA {tot:9.0f} | producer waits: A-empty {pct(1):4.1f}% B-empty {pct(2):4.1f}% "
-          f"| mma waits: A-full {pct(6):4.1f}% B-full {pct(7):4.1f}% tmem-empty {pct(8):4.1f}% "
-          f"| epi waits: tmem-full {pct(11):4.1f}% store-read {pct(12):4.1f}% bar {pct(13):4.1f}%")
+    print(f"{name:30s} {ms:7.3f} ms {flops / ms / 1e9:5.0f} TF/s cyc/CTA {tot:9.0f} | prod A-empty {pct(1):4.1f} B-empty {pct(2):4.1f} "
+          f"| mma A-full {pct(6):4.1f} B-full {pct(7):4.1f} tmem-empty {pct(8):4.1f} "
+          f"| epi tmem-full {pct(11):4.1f} tmem-ld {pct(12):4.1f} math {pct(13):4.1f} stage+store {pct(14):4.1f}")
 
 
 def conv_case(B, Cin, Cout, H, W, k=3, dil=1):

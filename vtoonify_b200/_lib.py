@@ -48,6 +48,7 @@ class SmallNDesc(Structure):
         ("skip", c_void_p), ("skip_kernel", c_void_p),
         ("out", c_void_p), ("mul_out", c_void_p), ("mul_src", c_void_p),
         ("mul_c", c_int32), ("round_tf32", c_int32),
+        ("tap_const", c_void_p),
     ]
 
 
@@ -73,6 +74,7 @@ SYMBOLS = {
     "vt_set_option": (c_int, [c_char_p, c_int]),
     "vt_set_debug_buffer": (c_int, [_P]),
     "vt_smalln_conv_f32": (c_int, [POINTER(SmallNDesc), _P]),
+    "vt_affine_fold_weights_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vt_fir_nhwc_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int,
                                 c_float, c_float, c_int, _P]),
     "vt_instnorm_ws_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),

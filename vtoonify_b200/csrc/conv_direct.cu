@@ -128,14 +128,16 @@ __global__ void __launch_bounds__(256)
 smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
   const vt_smalln_desc& d = args.d;
   extern __shared__ __align__(16) float smem[];
-  float* Ws = smem;                                  // [taps][N][src_c]
-  float* Wp = smem + (size_t)d.taps * N * d.src_c;   // [taps][N][n_planar]
+  const int CW = d.src2_mode ? 2 * d.src_c : d.src_c;           // weight-row channels (virtual concat doubles them)
+  float* Ws = smem;                                              // [taps][N][CW]
+  float* Wp = smem + (size_t)d.taps * N * CW;                    // [taps][N][n_planar]
   float* Ks = Wp + (size_t)d.taps * N * (d.n_planar > 0 ? d.n_planar : 0);  // [16] skip kernel
+  float* Tc = Ks + 16;                                           // [taps][N] per-tap constants (affine fold), optional
   const int b = blockIdx.y;
   const int wb = d.wB > 1 ? b : 0;
-  for (int i = threadIdx.x; i < d.taps * N * d.src_c; i += blockDim.x) {
-    const int c = i % d.src_c;
-    const int tn = i / d.src_c;
+  for (int i = threadIdx.x; i < d.taps * N * CW; i += blockDim.x) {
+    const int c = i % CW;
+    const int tn = i / CW;
     const int t = tn / N, n = tn % N;
     Ws[i] = d.weight[(((int64_t)wb * d.w_taps + d.tap_w[t]) * d.Cout + n) * d.w_cstride + c];
   }
@@ -148,48 +150,73 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
     }
   }
   if (d.skip && threadIdx.x < 16) Ks[threadIdx.x] = d.skip_kernel[threadIdx.x];
+  if (d.tap_const)
+    for (int i = threadIdx.x; i < d.taps * N; i += blockDim.x)
+      Tc[i] = d.tap_const[((int64_t)wb * d.w_taps + d.tap_w[i / N]) * d.Cout + (i % N)];
   __syncthreads();
 
-  // A warp owns 32 consecutive pixels.  They are processed 4 at a time (8 lanes x float4 = 32 channels of one pixel per
-  // load instruction, fully coalesced); the 4 reduced results of sub-iteration `it` are handed to lanes 4*it..4*it+3 so
-  // that afterwards lane L holds pixel L's outputs and every planar store / skip read is a coalesced 128-byte access.
+  // A block owns a patch of 8 rows x 32 columns (warp w <-> row w): the vertical taps of neighbouring warps hit the
+  // same L1 lines (1.25x re-read instead of 3x from L2).  Channels are walked in 32-wide chunks with the taps inside,
+  // so the L1 working set is ~10 rows x 34 px x 128 B.  A warp processes its 32 pixels 4 at a time (8 lanes x float4 =
+  // one pixel's 32-channel chunk per coalesced load); reduced results are handed to lane L <-> pixel L for the
+  // epilogue, so planar stores and skip reads are coalesced.
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7;      // channel slice
   const int grp = lane >> 3;     // pixel within the sub-iteration
   const int warp = threadIdx.x >> 5;
   const int64_t HW = (int64_t)d.H * d.W;
-  const int64_t runs = vt_cdiv(HW, 32);
+  const int patches_x = (d.W + 31) / 32;
+  const int patches_y = (d.H + 7) / 8;
   const int hs = d.H / 2, ws = d.W / 2;
-  for (int64_t run = (int64_t)blockIdx.x * 8 + warp; run < runs; run += (int64_t)gridDim.x * 8) {
-    const int64_t p0 = run * 32;
+  for (int patch = blockIdx.x; patch < patches_x * patches_y; patch += gridDim.x) {
+    const int y = (patch / patches_x) * 8 + warp;
+    const int x0 = (patch % patches_x) * 32;
+    const bool row_ok = y < d.H;
     float keep[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) keep[n] = 0.f;
     if (d.src_c > 0) {
-#pragma unroll 2
       for (int it = 0; it < 8; ++it) {
-        const int64_t p = p0 + it * 4 + grp;
-        const bool p_ok = p < HW;
-        const int y = p_ok ? (int)(p / d.W) : 0, x = p_ok ? (int)(p % d.W) : 0;
+        const int x = x0 + it * 4 + grp;
+        const bool p_ok = row_ok && x < d.W;
         float acc[N];
 #pragma unroll
         for (int n = 0; n < N; ++n) acc[n] = 0.f;
         if (p_ok) {
-          for (int t = 0; t < d.taps; ++t) {
-            const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
-            if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
-            const float* ap = d.src + (((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride;
-            const float* wt = Ws + (size_t)t * N * d.src_c;
-            for (int c = sub * 4; c < d.src_c; c += 32) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(ap + c));
+          for (int c = sub * 4; c < d.src_c; c += 32) {
+            for (int t = 0; t < d.taps; ++t) {
+              const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+              if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+              const int64_t po = (((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride + c;
+              const float4 a = __ldg(reinterpret_cast<const float4*>(d.src + po));
+              const float* wt = Ws + (size_t)t * N * CW + c;
 #pragma unroll
               for (int n = 0; n < N; ++n) {
-                const float4 w = *reinterpret_cast<const float4*>(wt + n * d.src_c + c);
+                const float4 w = *reinterpret_cast<const float4*>(wt + n * CW);
                 acc[n] = fmaf(a.x, w.x, acc[n]);
                 acc[n] = fmaf(a.y, w.y, acc[n]);
                 acc[n] = fmaf(a.z, w.z, acc[n]);
                 acc[n] = fmaf(a.w, w.w, acc[n]);
               }
+              if (d.src2_mode) {   // second half of the virtual concat: |src - src2|
+                const float4 e = __ldg(reinterpret_cast<const float4*>(d.src2 + po));
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                  const float4 w = *reinterpret_cast<const float4*>(wt + n * CW + d.src_c);
+                  acc[n] = fmaf(fabsf(a.x - e.x), w.x, acc[n]);
+                  acc[n] = fmaf(fabsf(a.y - e.y), w.y, acc[n]);
+                  acc[n] = fmaf(fabsf(a.z - e.z), w.z, acc[n]);
+                  acc[n] = fmaf(fabsf(a.w - e.w), w.w, acc[n]);
+                }
+              }
+            }
+          }
+          if (d.tap_const && sub == 0) {   // constant term of the folded affine (only in-bounds taps contribute)
+            for (int t = 0; t < d.taps; ++t) {
+              const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+              if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+#pragma unroll
+              for (int n = 0; n < N; ++n) acc[n] += Tc[t * N + n];
             }
           }
         }
@@ -205,10 +232,10 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
         }
       }
     }
-    // ---- per-pixel epilogue: lane L <-> pixel p0 + L
-    const int64_t p = p0 + lane;
-    const bool p_ok = p < HW;
-    const int y = p_ok ? (int)(p / d.W) : 0, x = p_ok ? (int)(p % d.W) : 0;
+    // ---- per-pixel epilogue: lane L <-> pixel (y, x0 + L)
+    const int x = x0 + lane;
+    const bool p_ok = row_ok && x < d.W;
+    const int64_t p = (int64_t)y * d.W + x;
     float m0v = 0.f;
     if (p_ok) {
       if (d.n_planar > 0) {
@@ -250,8 +277,9 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
     if (d.mul_out) {
       for (int it = 0; it < 8; ++it) {
         const float m = __shfl_sync(0xffffffffu, m0v, it * 4 + grp);
-        const int64_t pp = p0 + it * 4 + grp;
-        if (pp < HW) {
+        const int xx = x0 + it * 4 + grp;
+        if (row_ok && xx < d.W) {
+          const int64_t pp = (int64_t)y * d.W + xx;
           const float* ms = d.mul_src + ((int64_t)b * HW + pp) * d.mul_c;
           float* mo = d.mul_out + ((int64_t)b * HW + pp) * d.mul_c;
           for (int c = sub * 4; c < d.mul_c; c += 32) {
@@ -263,6 +291,38 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
         }
       }
     }
+  }
+}
+
+// Fold the AdaIN affine of Fusion.forward (model/vtoonify.py:125-126) into the mask-conv weights:
+//   conv(gamma*(x-mean)*rstd + beta, W) = conv(x, W*a) + sum_c W*bb   with a = gamma*rstd, bb = beta - gamma*mean*rstd,
+// the constant only for taps that fall inside the image (the reference zero-pads the normalised tensor).
+// grid (taps*N, B); w: [taps][N][C2]; stats: [B][C2][2]; gb: [B][2*C2]; out_w: [B][taps][N][C2]; out_k: [B][taps][N]
+__global__ void __launch_bounds__(256)
+affine_fold_kernel(const float* __restrict__ w, const float* __restrict__ stats, const float* __restrict__ gb,
+                   float* __restrict__ out_w, float* __restrict__ out_k, int C2) {
+  const int tn = blockIdx.x, b = blockIdx.y;
+  const float* wr = w + (int64_t)tn * C2;
+  const float* st = stats + (int64_t)b * C2 * 2;
+  const float* gamma = gb + (int64_t)b * 2 * C2;
+  const float* beta = gamma + C2;
+  float* ow = out_w + ((int64_t)b * gridDim.x + tn) * C2;
+  float k = 0.f;
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    const float a = gamma[c] * st[c * 2 + 1];
+    const float bb = beta[c] - a * st[c * 2];
+    ow[c] = wr[c] * a;
+    k = fmaf(wr[c], bb, k);
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) k += __shfl_xor_sync(0xffffffffu, k, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    out_k[(int64_t)b * gridDim.x + tn] = t;
   }
 }
 
@@ -329,7 +389,7 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   VT_CHECK(d->src_c == 0 || (d->src && aligned16(d->src)), "smalln_conv: bad src pointer");
   VT_CHECK(d->n_planar >= 0 && d->n_planar <= 4, "smalln_conv: n_planar must be <= 4");
   VT_CHECK(d->n_planar == 0 || (d->planar && d->planar_weight), "smalln_conv: planar source needs planar weights");
-  VT_CHECK(d->src2_mode == 0, "smalln_conv: src2_mode not supported");
+  VT_CHECK(d->src2_mode == 0 || (d->src2_mode == 1 && d->src2 && aligned16(d->src2)), "smalln_conv: bad src2 / src2_mode");
   VT_CHECK(d->wB == 1 || d->wB == d->B, "smalln_conv: wB must be 1 or B");
   VT_CHECK(d->weight || d->src_c == 0, "smalln_conv: null weight");
   VT_CHECK(d->act == VT_ACT_NONE || d->act == VT_ACT_RELU_TANH, "smalln_conv: bad act");
@@ -340,10 +400,12 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
 
   SmallNArgs a;
   a.d = *d;
-  const size_t smem = ((size_t)d->taps * d->Cout * (d->src_c + d->n_planar) + 16) * sizeof(float);
+  const int cw = d->src2_mode ? 2 * d->src_c : d->src_c;
+  VT_CHECK(d->src_c == 0 || d->w_cstride >= cw, "smalln_conv: weight row shorter than the (virtual-concat) channel count");
+  const size_t smem = ((size_t)d->taps * d->Cout * (cw + d->n_planar + 1) + 16) * sizeof(float);
   VT_CHECK(smem <= 200 * 1024, "smalln_conv: weights (%zu B) do not fit in shared memory", smem);
   const int64_t HW = (int64_t)d->H * d->W;
-  int64_t blocks = vt_cdiv(vt_cdiv(HW, 32), 8);
+  int64_t blocks = vt_cdiv(d->W, 32) * vt_cdiv(d->H, 8);
   const int64_t cap = (int64_t)vt_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)d->B);
@@ -361,6 +423,15 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
     default: VT_LAUNCH_SMALLN(4); break;
   }
 #undef VT_LAUNCH_SMALLN
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_affine_fold_weights_f32(const float* w, const float* stats, const float* gamma_beta, float* out_w, float* out_k,
+                                          int B, int taps_n, int C2, void* stream) {
+  VT_CHECK(w && stats && gamma_beta && out_w && out_k && B >= 1 && B <= 65535 && taps_n >= 1 && C2 >= 1, "affine_fold_weights: bad args");
+  dim3 grid((unsigned)taps_n, (unsigned)B);
+  affine_fold_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, stats, gamma_beta, out_w, out_k, C2);
   VT_LAUNCH_CHECK();
   return 0;
 }

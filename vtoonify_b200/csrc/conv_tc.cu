@@ -43,11 +43,12 @@ struct TcArgs {
   int n_steps;
   int8_t step_view[VT_MAX_TAPS], step_vx[VT_MAX_TAPS], step_vy[VT_MAX_TAPS];
   int16_t step_w[VT_MAX_TAPS];
+  int step_aoff[VT_MAX_TAPS];                  // halo mode: byte offset of the tap's first row inside the halo box
   int mt, n_phase, acc_stages;                 // mt accumulators (M tiles) of block_n columns per work item; n_phase: the N
                                                // dimension is phase-major [n_phase][Cout] (folded up-conv), else 1
   int tgroup;                                  // taps per weight TMA box / pipeline step (consecutive slabs)
   int halo, halo_x0, halo_y0, halo_w;
-  int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes;
+  int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   int block_n, n_tiles, tiles_x, tiles_y, B, total_tiles, tmem_cols;
   int Ho, Wo, Cout, wB, out_cpitch;
   const float* bias;
@@ -55,6 +56,7 @@ struct TcArgs {
   const float* noise_w;
   const float* res;
   int64_t out_sb, out_sy, out_sx, phase_off[4];
+  int64_t pix_sb, pix_sy, pix_sx, phase_pix[4];   // the same view in dense-pixel units (noise index), = offsets / out_cpitch
   int act, round_tf32;
   float slope, gain, alpha, beta;
   unsigned long long* dbg;   // optional [grid][16] cycle counters (tuning only)
@@ -114,7 +116,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     // ================= TMA producer (whole warp converged; one elected lane issues) =================
     // Issuing from a converged warp lets ptxas keep descriptors/coordinates in uniform registers; issuing from a
     // `lane == 0` branch wraps every UTMALDG/UTCHMMA in an ELECT loop (measured 103 vs 59 cycles per MMA).
-    uint32_t a_it = 0, b_it = 0;
+    // ring positions are kept as (stage, parity) pairs and advanced incrementally: runtime-divisor % and / cost ~50-100
+    // cycles each on the issuing thread's critical path
+    int a_st = 0, b_st = 0;
+    uint32_t a_par = 0, b_par = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
@@ -125,38 +130,37 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
         for (int kc = 0; kc < p.kchunks[s]; ++kc) {
           const int c0 = kc * KCH;
           if (p.halo) {
-            const int st = a_it % p.a_stages;
-            VT_TWAIT(0, mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 1));
+            VT_TWAIT(0, mbar_wait(a_empty(a_st), a_par ^ 1, 1));
             if (elect_one()) {
-              mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
-              tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][0], a_full(st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+              mbar_arrive_expect_tx(a_full(a_st), (uint32_t)p.a_tx_bytes);
+              tma_load_4d(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
             }
             __syncwarp();
-            ++a_it;
+            if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
           }
+          int gj = 0;   // position inside the current tap group
           for (int j = 0; j < p.n_steps; ++j) {
             if (!p.halo) {
-              const int st = a_it % p.a_stages;
-              VT_TWAIT(0, mbar_wait(a_empty(st), ((a_it / p.a_stages) & 1) ^ 1, 2));
+              VT_TWAIT(0, mbar_wait(a_empty(a_st), a_par ^ 1, 2));
               if (elect_one()) {
-                mbar_arrive_expect_tx(a_full(st), (uint32_t)p.a_tx_bytes);
-                tma_load_4d(a_base + st * p.a_stage_bytes, &p.in_map[s][p.step_view[j]], a_full(st), c0, ox0 + p.step_vx[j],
+                mbar_arrive_expect_tx(a_full(a_st), (uint32_t)p.a_tx_bytes);
+                tma_load_4d(a_base + a_st * p.a_stage_bytes, &p.in_map[s][p.step_view[j]], a_full(a_st), c0, ox0 + p.step_vx[j],
                             oy0 + p.step_vy[j], b);
               }
               __syncwarp();
-              ++a_it;
+              if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
             }
-            if (j % p.tgroup == 0) {
+            if (gj == 0) {
               // one TMA box carries the weight tiles of `tgroup` consecutive taps: (32 ch, block_n, tgroup, 1)
-              const int st = b_it % p.b_stages;
-              VT_TWAIT(1, mbar_wait(b_empty(st), ((b_it / p.b_stages) & 1) ^ 1, 3));
+              VT_TWAIT(1, mbar_wait(b_empty(b_st), b_par ^ 1, 3));
               if (elect_one()) {
-                mbar_arrive_expect_tx(b_full(st), (uint32_t)(p.block_n * 128 * p.tgroup));
-                tma_load_4d(b_base + st * p.b_stage_bytes, &p.w_map, b_full(st), p.coff[s] + c0, n0, p.step_w[j], wb);
+                mbar_arrive_expect_tx(b_full(b_st), (uint32_t)p.b_tx_bytes);
+                tma_load_4d(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), p.coff[s] + c0, n0, p.step_w[j], wb);
               }
               __syncwarp();
-              ++b_it;
+              if (++b_st == p.b_stages) { b_st = 0; b_par ^= 1; }
             }
+            if (++gj == p.tgroup) gj = 0;
           }
         }
       }
@@ -164,42 +168,39 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp converged; one elected lane issues) =================
     const uint32_t idesc = make_idesc_tf32(TILE_M, p.block_n);
-    uint32_t a_it = 0, b_it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const int as = lt % p.acc_stages;
-      VT_TWAIT(2, mbar_wait(t_empty(as), ((lt / p.acc_stages) & 1) ^ 1, 4));
+    int a_st = 0, b_st = 0, as = 0;
+    uint32_t a_par = 0, b_par = 0, t_par = 0;
+    const uint32_t tile_bytes_n = (uint32_t)p.block_n * 128u;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      VT_TWAIT(2, mbar_wait(t_empty(as), t_par ^ 1, 4));
       tc_fence_after();
       const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * p.mt * p.block_n);
       uint32_t first = 1;   // first K step of this work item overwrites the accumulators
       for (int s = 0; s < p.n_src; ++s) {
         for (int kc = 0; kc < p.kchunks[s]; ++kc) {
-          int sta = 0;
           if (p.halo) {
-            sta = a_it % p.a_stages;
-            VT_TWAIT(0, mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 5));
+            VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 5));
           }
+          int gj = 0;
           for (int j = 0; j < p.n_steps; ++j) {
             if (!p.halo) {
-              sta = a_it % p.a_stages;
-              VT_TWAIT(0, mbar_wait(a_full(sta), (a_it / p.a_stages) & 1, 6));
+              VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 6));
             }
-            const int stb = b_it % p.b_stages;
-            if (j % p.tgroup == 0) {
-              VT_TWAIT(1, mbar_wait(b_full(stb), (b_it / p.b_stages) & 1, 7));
+            if (gj == 0) {
+              VT_TWAIT(1, mbar_wait(b_full(b_st), b_par, 7));
             }
             tc_fence_after();
-            uint32_t a_addr = a_base + sta * p.a_stage_bytes;
+            uint32_t a_addr = a_base + a_st * p.a_stage_bytes;
             uint32_t sbo = 1024;
             if (p.halo) {
               // The 128B swizzle is a function of the absolute smem address bits (TMA wrote the halo box with the
               // same function), so a tap is just a start address shifted by whole 128-byte rows; the descriptor's
               // base-offset field stays 0 (setting it to (addr>>7)&7 was measured WRONG on B200).
-              a_addr += (uint32_t)(((p.step_vy[j] - p.halo_y0) * p.halo_w + (p.step_vx[j] - p.halo_x0)) * 128);
+              a_addr += (uint32_t)p.step_aoff[j];
               sbo = (uint32_t)p.halo_w * 128u;
             }
-            const uint64_t bdesc = make_smem_desc_sw128(
-                b_base + stb * p.b_stage_bytes + (uint32_t)((j % p.tgroup) * p.block_n * 128), 1024, 0);
-            const bool last_of_group = (j % p.tgroup == p.tgroup - 1);
+            const uint64_t bdesc = make_smem_desc_sw128(b_base + b_st * p.b_stage_bytes + (uint32_t)gj * tile_bytes_n, 1024, 0);
+            const bool last_of_group = (gj == p.tgroup - 1);
             if (elect_one()) {
               for (int g = 0; g < p.mt; ++g) {
                 const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)(g * TILE_W * 128), sbo, 0);
@@ -209,23 +210,24 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 umma_tf32(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
                 umma_tf32(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
               }
-              if (last_of_group) umma_commit(b_empty(stb));
-              if (!p.halo) umma_commit(a_empty(sta));
+              if (last_of_group) umma_commit(b_empty(b_st));
+              if (!p.halo) umma_commit(a_empty(a_st));
             }
             __syncwarp();
             first = 0;
-            if (last_of_group) ++b_it;
-            if (!p.halo) ++a_it;
+            if (last_of_group) { gj = 0; if (++b_st == p.b_stages) { b_st = 0; b_par ^= 1; } } else { ++gj; }
+            if (!p.halo) { if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; } }
           }
           if (p.halo) {
-            if (elect_one()) umma_commit(a_empty(sta));
+            if (elect_one()) umma_commit(a_empty(a_st));
             __syncwarp();
-            ++a_it;
+            if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
           }
         }
       }
       if (elect_one()) umma_commit(t_full(as));
       __syncwarp();
+      if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
@@ -234,43 +236,62 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     const int ty = r / TILE_W, tx = r % TILE_W;
     const bool store_thread = (threadIdx.x == 128);
     const float nw = (p.noise && p.noise_w) ? *p.noise_w : 0.f;
-    uint32_t lt = 0, chunk = 0;
+    uint32_t chunk = 0;
     const int nchunks = p.block_n / 32;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    int as = 0;
+    uint32_t t_par = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
       const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w;
       const int n0 = n_tile * p.block_n;
-      const int as = lt % p.acc_stages;
-      VT_TWAIT(0, mbar_wait(t_full(as), (lt / p.acc_stages) & 1, 8));
+      VT_TWAIT(0, mbar_wait(t_full(as), t_par, 8));
       tc_fence_after();
+      const int ph0 = n0 / p.Cout, nb0 = n0 - ph0 * p.Cout;   // once per work item
       for (int g = 0; g < p.mt; ++g) {
         const int oy = oy0 + ty, ox = ox0 + g * TILE_W + tx;
         const bool in_img = oy < p.Ho && ox < p.Wo;
         const int64_t off0 = (int64_t)b * p.out_sb + (int64_t)oy * p.out_sy + (int64_t)ox * p.out_sx;
+        const int64_t pix0 = (int64_t)b * p.pix_sb + (int64_t)oy * p.pix_sy + (int64_t)ox * p.pix_sx;   // dense-pixel index
+        int ph = ph0, nb = nb0 - 32;
         for (int j = 0; j < nchunks; ++j, ++chunk) {
           // column -> (phase, channel): the N dimension is phase-major [n_phase][Cout]; a 32-column chunk never straddles
-          const int ncol = n0 + j * 32;
-          const int ph = ncol / p.Cout;
-          const int nb = ncol - ph * p.Cout;
+          nb += 32;
+          if (nb >= p.Cout) { nb -= p.Cout; ++ph; }
           const int64_t off = p.phase_off[ph] + off0;
-          const float nz = (p.noise && in_img) ? nw * p.noise[off / p.out_cpitch] : 0.f;
+          const float nz = (p.noise && in_img) ? nw * p.noise[p.phase_pix[ph] + pix0] : 0.f;
           float v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.block_n + j * 32), v);
+          VT_TWAIT(1, tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.block_n + j * 32), v));
+          const long long t_math0 = p.dbg ? clock64() : 0;
           if (g == p.mt - 1 && j == nchunks - 1) {
             // every accumulator of this stage is in registers: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty(as));
           }
+          // straight-line math: the 32 bias values come in as 8 vector loads issued together (a per-element __ldg inside a
+          // branchy loop serialised 32 L1 latencies: ~4k cycles per chunk, measured), and the activation is selected
+          // outside the element loop
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
+            float4 bq[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = v[i];
-            if (p.noise) x += nz;
-            if (p.bias) x += __ldg(p.bias + nb + i);
-            if (p.act == VT_ACT_LRELU) x = vt_lrelu(x, p.slope) * p.gain;
-            else if (p.act == VT_ACT_RELU_TANH) x = tanhf(fmaxf(x, 0.f));
-            v[i] = x;
+            for (int i = 0; i < 8; ++i) bq[i] = __ldg(bp + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i + 0] += bq[i].x; v[4 * i + 1] += bq[i].y; v[4 * i + 2] += bq[i].z; v[4 * i + 3] += bq[i].w;
+            }
+          }
+          if (p.noise) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += nz;
+          }
+          if (p.act == VT_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = vt_lrelu(v[i], p.slope) * p.gain;
+          } else if (p.act == VT_ACT_RELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = tanhf(fmaxf(v[i], 0.f));
           }
           if (p.res) {
             if (in_img) {
@@ -292,9 +313,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = vt_round_tf32(v[i]);
           }
+          if (p.dbg) tw[2] += clock64() - t_math0;
+          const long long t_st0 = p.dbg ? clock64() : 0;
           const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
-          if (store_thread) VT_TWAIT(1, tma_store_wait_read<1>());   // the store that used this buffer two chunks ago has read it
-          VT_TWAIT(2, named_bar_sync(1, 128));
+          if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
+          named_bar_sync(1, 128);
           const uint32_t row = sbuf + (uint32_t)r * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -309,8 +332,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             tma_store_4d(&p.out_map[ph], sbuf, nb, ox0 + g * TILE_W, oy0, b);
             tma_store_commit();
           }
+          if (p.dbg) tw[3] += clock64() - t_st0;
         }
       }
+      if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
     if (store_thread) tma_store_wait_all<0>();
   }
@@ -385,6 +410,7 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
+  VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
   return 1;
 #undef VT_SUP
 }
@@ -416,6 +442,15 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.bias = d->bias; a.noise = d->noise; a.noise_w = d->noise_w; a.res = d->res;
   a.out_sb = d->out_sb; a.out_sy = d->out_sy; a.out_sx = d->out_sx;
   for (int ph = 0; ph < 4; ++ph) a.phase_off[ph] = d->phase_off[ph < d->n_phase ? ph : 0];
+  if (d->noise) {
+    VT_CHECK(d->out_sb % d->out_cpitch == 0 && d->out_sy % d->out_cpitch == 0 && d->out_sx % d->out_cpitch == 0,
+             "conv_tc: output strides must be multiples of out_cpitch when noise is used");
+    a.pix_sb = d->out_sb / d->out_cpitch; a.pix_sy = d->out_sy / d->out_cpitch; a.pix_sx = d->out_sx / d->out_cpitch;
+    for (int ph = 0; ph < 4; ++ph) {
+      VT_CHECK(a.phase_off[ph] % d->out_cpitch == 0, "conv_tc: phase offset must be a multiple of out_cpitch");
+      a.phase_pix[ph] = a.phase_off[ph] / d->out_cpitch;
+    }
+  }
   a.dbg = g_tc_dbg;
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;
@@ -472,6 +507,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     }
   }
   a.tgroup = tgroup;
+  a.b_tx_bytes = bn * 128 * tgroup;
   for (;; mt /= 2) {
     const int halo_w = TILE_W * mt + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
     const int halo_bytes = halo_w * halo_h * 128;
@@ -496,6 +532,8 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   }
   VT_CHECK(smem_bytes <= MAX_SMEM && a.a_stages >= 2 && a.b_stages >= 2 && a.a_stages <= 8 && a.b_stages <= 8,
            "conv_tc: shared memory plan does not fit (%d B, mt=%d, bn=%d)", smem_bytes, mt, bn);
+  for (int t = 0; t < d->taps; ++t)
+    a.step_aoff[t] = ((a.step_vy[t] - a.halo_y0) * a.halo_w + (a.step_vx[t] - a.halo_x0)) * 128;
   a.mt = mt;
   a.acc_stages = (2 * mt * bn <= 512) ? 2 : 1;
   int tc = 32;

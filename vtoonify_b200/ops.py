@@ -368,9 +368,12 @@ def fir_nhwc(x: torch.Tensor, kernel: torch.Tensor, pad: Tuple[int, int], bias: 
 def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], taps, Cout: int, B: int, H: int, W: int,
                 planar: Optional[torch.Tensor] = None, planar_weight: Optional[torch.Tensor] = None,
                 bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, skip: Optional[torch.Tensor] = None,
-                skip_kernel: Optional[torch.Tensor] = None, mul_src: Optional[torch.Tensor] = None):
-    """Cout<=4 convolution with planar NCHW output ``[B,Cout,H,W]``; optionally also returns ``mul_src * out[:,0]``."""
-    _req_cuda(src, weight, planar, planar_weight, bias, skip, skip_kernel, mul_src)
+                skip_kernel: Optional[torch.Tensor] = None, mul_src: Optional[torch.Tensor] = None,
+                src2: Optional[torch.Tensor] = None, tap_const: Optional[torch.Tensor] = None):
+    """Cout<=4 convolution with planar NCHW output ``[B,Cout,H,W]``; optionally also returns ``mul_src * out[:,0]``.
+    ``src2``: the input is the virtual concat ``[src | abs(src - src2)]`` (weight rows hold 2*C channels);
+    ``tap_const`` ``[wB, w_taps, Cout]``: constant added for every in-bounds tap (folded AdaIN affine)."""
+    _req_cuda(src, weight, planar, planar_weight, bias, skip, skip_kernel, mul_src, src2, tap_const)
     dev = (src if src is not None else planar).device
     d = SmallNDesc()
     d.struct_size = _lib.ctypes.sizeof(SmallNDesc)
@@ -385,6 +388,12 @@ def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], tap
         d.src_cstride = src.shape[3]
         d.weight = weight.data_ptr()
         d.wB, d.w_taps, _, d.w_cstride = weight.shape
+        if src2 is not None:
+            if src2.shape != src.shape or not src2.is_contiguous():
+                raise _lib.VtError("smalln_conv: src2 must match src")
+            d.src2, d.src2_mode = src2.data_ptr(), 1
+        if tap_const is not None:
+            d.tap_const = tap_const.contiguous().data_ptr()
     else:
         d.wB, d.w_taps = 1, (planar_weight.shape[0] if planar_weight is not None else 1)
     d.Cout = Cout
@@ -437,6 +446,18 @@ def adain_apply(x: torch.Tensor, stats: torch.Tensor, gamma_beta: torch.Tensor, 
     check(_lib.load().vt_adain_apply_nhwc(x.data_ptr(), _ptr(x2), mode, B, H * W, C, C, stats.data_ptr(),
                                           gamma_beta.contiguous().data_ptr(), out.data_ptr(), _round_flag(), _stream()))
     return out
+
+
+def affine_fold_weights(w: torch.Tensor, stats: torch.Tensor, gamma_beta: torch.Tensor):
+    """Fold AdaIN's per-(b,c) affine into conv weights ``w`` [1, taps, N, C2] -> (w' [B, taps, N, C2], k [B, taps, N])."""
+    _req_cuda(w, stats, gamma_beta)
+    _, taps, N, C2 = w.shape
+    B = stats.shape[0]
+    out_w = torch.empty((B, taps, N, C2), device=w.device, dtype=torch.float32)
+    out_k = torch.empty((B, taps, N), device=w.device, dtype=torch.float32)
+    check(_lib.load().vt_affine_fold_weights_f32(w.data_ptr(), stats.data_ptr(), gamma_beta.contiguous().data_ptr(),
+                                                 out_w.data_ptr(), out_k.data_ptr(), B, taps * N, C2, _stream()))
+    return out_w, out_k
 
 
 def axpby(a: torch.Tensor, b: Optional[torch.Tensor], sa: float, sb: float = 0.0, round_tf32: Optional[bool] = None) -> torch.Tensor:

@@ -131,8 +131,16 @@ class Fusion(nn.Module):
         B = f_G.shape[0]
         label = torch.full((B, 1), float(d_s), device=f_G.device, dtype=torch.float32)
         label = self.linear[2](self.linear[0](label))           # LeakyReLUs are fused into the Linears
-        normed = self.norm.forward_nhwc(f_G, label, x2=f_E)      # AdaIN(cat(f_G, |f_G - f_E|))
-        m_E, fEm = self.conv2.forward_smalln(normed, act=ACT_RELU_TANH, mul_src=f_E)
+        # AdaIN(cat(f_G, |f_G - f_E|)) is never materialised: plane statistics in one pass over (f_G, f_E), the affine
+        # folded into per-sample mask-conv weights, and the mask conv reads f_G / f_E directly (virtual concat)
+        stats = ops.instnorm_stats(f_G, f_E)
+        gb = self.norm.style(label)
+        C2 = 2 * f_G.shape[3]
+        w_plain = self.conv2._wp.get(self.conv2.weight, 1.0, C2, round_tf32=False)          # [1, 9, 1, 2C]
+        w_fold, k_fold = ops.affine_fold_weights(w_plain, stats, gb)
+        B, H, W, _ = f_G.shape
+        m_E, fEm = ops.smalln_conv(f_G, w_fold, ops.conv_taps(3, 1), 1, B, H, W, bias=self.conv2.bias, act=ACT_RELU_TANH,
+                                   mul_src=f_E, src2=f_E, tap_const=k_fold)
         f_out = self.conv.forward_nhwc(f_G, x2=fEm)
         return f_out, m_E, fEm
 

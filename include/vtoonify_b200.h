@@ -129,6 +129,14 @@ typedef struct vt_conv_desc {
   float   alpha, beta;
   int32_t round_tf32;           /* round outputs to TF32 (rna) for a tensor-core consumer       */
   int32_t reserved;
+  /* optional fused ToRGB tail (tensor-core kernel only, needs Cout <= 256, n_phase == 1, dense output):
+   * rgb_out[b,c,oy,ox] = sum_n out[b,oy,ox,n] * rgb_w[b,c,n] + rgb_bias[c] + upfirdn2d(rgb_skip, rgb_skip_kernel, up=2, pad=(2,1))
+   * (model/stylegan/model.py:383-392 on the freshly computed activation, which is not re-read from HBM) */
+  const float* rgb_w;           /* [wB][3][Cout] modulated 1x1 weights, or NULL                  */
+  const float* rgb_bias;        /* [3]                                                           */
+  const float* rgb_skip;        /* planar [B,3,Ho/2,Wo/2] or NULL                                */
+  const float* rgb_skip_kernel; /* [4,4]                                                         */
+  float*       rgb_out;         /* planar [B,3,Ho,Wo]                                            */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */

@@ -224,3 +224,28 @@ def test_folded_upconv(shape):
     ops.set_precision("tf32")
     assert maxerr(ops.to_nchw(t).cpu(), ops.to_nchw(a).cpu()) <= 2e-5 * max(1.0, ref.abs().max().item())
     assert maxerr(ops.to_nchw(t).cpu(), ref) <= 5e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cg2", [0, 1])
+@pytest.mark.parametrize("case", [CASES[3], CASES[4], (2, 256, 256, 40, 24, 3, 1, 1, 1), (1, 512, 512, 16, 16, 3, 1, 4, 4),
+                                  (2, 64, 256, 17, 9, 3, 1, 1, 1)])
+def test_tc_cta_pairs(case, cg2):
+    """cta_group::2 (CTA pair, M = 256) vs single-CTA tcgen05 vs the FFMA kernel on N-tile-256 layers."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007)
+    x = tf32_exact((B, Cin, H, W), g)
+    w = tf32_exact((Cout, Cin, k, k), g, 1.0 / 8)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn((B, Cout, H, W), generator=g)
+    ops.set_precision("fp32")
+    kw = dict(act=_lib.ACT_LRELU, slope=0.2, gain=1.25, alpha=0.5, beta=0.75)
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    old = _lib.load().vt_set_option(b"tc_cg2", cg2)
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "tf32", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    finally:
+        _lib.load().vt_set_option(b"tc_cg2", old)
+        ops.set_precision("tf32")
+    scale = ref.abs().max().item()
+    assert maxerr(y, ref) <= 2e-5 * max(1.0, scale), f"cg2 {cg2}: err {maxerr(y, ref):.3e} (scale {scale:.1f})"

@@ -18,6 +18,7 @@ for mode in 0 1; do
 done
 run conv_tc_misc 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "epilogue or concat or polyphase or budget"
 run conv_tc_mt 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "m_tiles"
+run conv_tc_pairs 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "cta_pairs"
 run conv_tc_fold 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "folded"
 run layers 900 python -m pytest tests/test_gpu_layers.py -q -m gpu -s
 run vtoonify 900 python -m pytest tests/test_gpu_vtoonify.py -q -m gpu -s

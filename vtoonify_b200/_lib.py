@@ -32,6 +32,8 @@ class ConvDesc(Structure):
         ("act", c_int32), ("slope", c_float), ("gain", c_float),
         ("res", c_void_p), ("alpha", c_float), ("beta", c_float),
         ("round_tf32", c_int32), ("reserved", c_int32),
+        ("rgb_w", c_void_p), ("rgb_bias", c_void_p), ("rgb_skip", c_void_p), ("rgb_skip_kernel", c_void_p),
+        ("rgb_out", c_void_p),
     ]
 
 
@@ -105,8 +107,8 @@ def load():
         fn.argtypes = args
     if lib.vt_abi_version() != 1:
         raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects 1")
-    for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup")):
-        if os.environ.get(env):
+    for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup"), ("VT_TC_CG2", b"tc_cg2")):
+        if os.environ.get(env) is not None and os.environ.get(env) != "":
             lib.vt_set_option(key, int(os.environ[env]))      # tuning experiments only
     _lib = lib
     return lib

@@ -176,53 +176,77 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
 #pragma unroll
     for (int n = 0; n < N; ++n) keep[n] = 0.f;
     if (d.src_c > 0) {
-      for (int it = 0; it < 8; ++it) {
-        const int x = x0 + it * 4 + grp;
-        const bool p_ok = row_ok && x < d.W;
-        float acc[N];
+      // acc[it][n]: the 8 sub-iterations (4 pixels each) are kept live together so that every (channel chunk, tap) step
+      // issues 8 independent 16-byte loads per lane before any FMA consumes them (memory-level parallelism)
+      float acc[8][N];
 #pragma unroll
-        for (int n = 0; n < N; ++n) acc[n] = 0.f;
-        if (p_ok) {
-          for (int c = sub * 4; c < d.src_c; c += 32) {
-            for (int t = 0; t < d.taps; ++t) {
-              const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
-              if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
-              const int64_t po = (((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride + c;
-              const float4 a = __ldg(reinterpret_cast<const float4*>(d.src + po));
-              const float* wt = Ws + (size_t)t * N * CW + c;
+      for (int it = 0; it < 8; ++it)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[it][n] = 0.f;
+      if (row_ok) {
+        for (int c = sub * 4; c < d.src_c; c += 32) {
+          for (int t = 0; t < d.taps; ++t) {
+            const int iy = y + d.tap_dy[t];
+            if (iy < 0 || iy >= d.H) continue;
+            const int ixb = x0 + grp + d.tap_dx[t];
+            const int64_t rowo = (((int64_t)b * d.H + iy) * d.W) * d.src_cstride + c;
+            float4 a[8], e[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int ix = ixb + it * 4;
+              const bool ok = ix >= 0 && ix < d.W && (ix - d.tap_dx[t]) < d.W;
+              a[it] = ok ? __ldg(reinterpret_cast<const float4*>(d.src + rowo + (int64_t)ix * d.src_cstride))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (d.src2_mode)
+                e[it] = ok ? __ldg(reinterpret_cast<const float4*>(d.src2 + rowo + (int64_t)ix * d.src_cstride))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float* wt = Ws + (size_t)t * N * CW + c;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+              const float4 w = *reinterpret_cast<const float4*>(wt + n * CW);
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                acc[it][n] = fmaf(a[it].x, w.x, acc[it][n]);
+                acc[it][n] = fmaf(a[it].y, w.y, acc[it][n]);
+                acc[it][n] = fmaf(a[it].z, w.z, acc[it][n]);
+                acc[it][n] = fmaf(a[it].w, w.w, acc[it][n]);
+              }
+            }
+            if (d.src2_mode) {   // second half of the virtual concat: |src - src2| (zero outside the image: a = e = 0)
 #pragma unroll
               for (int n = 0; n < N; ++n) {
-                const float4 w = *reinterpret_cast<const float4*>(wt + n * CW);
-                acc[n] = fmaf(a.x, w.x, acc[n]);
-                acc[n] = fmaf(a.y, w.y, acc[n]);
-                acc[n] = fmaf(a.z, w.z, acc[n]);
-                acc[n] = fmaf(a.w, w.w, acc[n]);
-              }
-              if (d.src2_mode) {   // second half of the virtual concat: |src - src2|
-                const float4 e = __ldg(reinterpret_cast<const float4*>(d.src2 + po));
+                const float4 w = *reinterpret_cast<const float4*>(wt + n * CW + d.src_c);
 #pragma unroll
-                for (int n = 0; n < N; ++n) {
-                  const float4 w = *reinterpret_cast<const float4*>(wt + n * CW + d.src_c);
-                  acc[n] = fmaf(fabsf(a.x - e.x), w.x, acc[n]);
-                  acc[n] = fmaf(fabsf(a.y - e.y), w.y, acc[n]);
-                  acc[n] = fmaf(fabsf(a.z - e.z), w.z, acc[n]);
-                  acc[n] = fmaf(fabsf(a.w - e.w), w.w, acc[n]);
+                for (int it = 0; it < 8; ++it) {
+                  acc[it][n] = fmaf(fabsf(a[it].x - e[it].x), w.x, acc[it][n]);
+                  acc[it][n] = fmaf(fabsf(a[it].y - e[it].y), w.y, acc[it][n]);
+                  acc[it][n] = fmaf(fabsf(a[it].z - e[it].z), w.z, acc[it][n]);
+                  acc[it][n] = fmaf(fabsf(a[it].w - e[it].w), w.w, acc[it][n]);
                 }
               }
             }
           }
-          if (d.tap_const && sub == 0) {   // constant term of the folded affine (only in-bounds taps contribute)
-            for (int t = 0; t < d.taps; ++t) {
-              const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
-              if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+        }
+        if (d.tap_const && sub == 0) {   // constant term of the folded affine (only in-bounds taps contribute)
+          for (int t = 0; t < d.taps; ++t) {
+            const int iy = y + d.tap_dy[t];
+            if (iy < 0 || iy >= d.H) continue;
 #pragma unroll
-              for (int n = 0; n < N; ++n) acc[n] += Tc[t * N + n];
+            for (int it = 0; it < 8; ++it) {
+              const int ix = x0 + it * 4 + grp + d.tap_dx[t];
+              if (ix < 0 || ix >= d.W) continue;
+#pragma unroll
+              for (int n = 0; n < N; ++n) acc[it][n] += Tc[t * N + n];
             }
           }
         }
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-          float v = acc[n];
+          float v = acc[it][n];
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -356,6 +380,7 @@ static int validate_conv_desc(const vt_conv_desc* d, const char* who) {
   }
   VT_CHECK(d->act >= 0 && d->act <= 2, "%s: bad act", who);
   if (d->noise) VT_CHECK(d->noise_w != nullptr, "%s: noise without noise_w", who);
+  if (d->rgb_w) VT_CHECK(d->rgb_out && d->rgb_bias && (!d->rgb_skip || d->rgb_skip_kernel), "%s: incomplete fused ToRGB arguments", who);
   return 0;
 }
 int vt_validate_conv_desc(const vt_conv_desc* d, const char* who) { return validate_conv_desc(d, who); }
@@ -363,6 +388,7 @@ int vt_validate_conv_desc(const vt_conv_desc* d, const char* who) { return valid
 extern "C" int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream) {
   if (validate_conv_desc(d, "conv2d_direct")) return 1;
   VT_CHECK(d->B <= 65535 && vt_cdiv(d->Cout, BN) <= 65535, "conv2d_direct: grid too large");
+  VT_CHECK(!d->rgb_w, "conv2d_direct: the fused ToRGB tail exists only in the tensor-core kernel");
   const int64_t HoWo = (int64_t)d->Ho * d->Wo;
   dim3 grid((unsigned)vt_cdiv(HoWo, BM), (unsigned)vt_cdiv(d->Cout, BN), (unsigned)d->B);
   for (int ph = 0; ph < d->n_phase; ++ph) {   // one launch per output phase (weight rows ph*Cout.., view offset phase_off[ph])

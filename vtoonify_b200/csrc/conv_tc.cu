@@ -47,6 +47,7 @@ struct TcArgs {
   int mt, n_phase, acc_stages;                 // mt accumulators (M tiles) of block_n columns per work item; n_phase: the N
                                                // dimension is phase-major [n_phase][Cout] (folded up-conv), else 1
   int tgroup;                                  // taps per weight TMA box / pipeline step (consecutive slabs)
+  int grp_first_mask, grp_last_mask;           // bit t: tap t is the first / last of its weight box (n_steps <= 32)
   int halo, halo_x0, halo_y0, halo_w;
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   int block_n, n_tiles, tiles_x, tiles_y, B, total_tiles, tmem_cols;
@@ -60,10 +61,16 @@ struct TcArgs {
   int act, round_tf32;
   float slope, gain, alpha, beta;
   unsigned long long* dbg;   // optional [grid][16] cycle counters (tuning only)
+  // fused ToRGB tail
+  const float* rgb_w; const float* rgb_bias; const float* rgb_skip; const float* rgb_skip_kernel; float* rgb_out;
 };
 
 #define VT_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
 
+// CG = 1: one CTA per work item (M = 128).  CG = 2: a CTA pair (cluster of 2) shares one tcgen05.mma.cta_group::2 with
+// M = 256: each CTA stages the activations of its own 128 pixels and HALF of every weight tile, so per-SM shared-memory
+// traffic (TMA writes + tensor-core operand reads) drops from ~160 to ~100 B/clk; rank 0 issues the MMAs for both.
+template <int CG>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -84,6 +91,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;      // CTA rank in the pair
+  const int cta_i = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int cta_n = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   long long tw[4] = {0, 0, 0, 0};
   const long long t_begin = clock64();
 
@@ -96,21 +106,23 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4 * CG); }
     fence_barrier_init();
     fence_proxy_async_smem();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
   }
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
-  const int item_w = TILE_W * p.mt;             // output columns covered by one work item
+  const int item_w = TILE_W * p.mt * CG;        // output columns covered by one work item (of the CTA pair if CG == 2)
+  const int rank_x = (int)rank * TILE_W * p.mt; // this CTA's column offset inside the work item
 
   if (warp == 0) {
     // ================= TMA producer (whole warp converged; one elected lane issues) =================
@@ -120,10 +132,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     // cycles each on the issuing thread's critical path
     int a_st = 0, b_st = 0;
     uint32_t a_par = 0, b_par = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
-      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w;
+      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
       const int wb = p.wB > 1 ? b : 0;
       for (int s = 0; s < p.n_src; ++s) {
@@ -132,8 +144,13 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           if (p.halo) {
             VT_TWAIT(0, mbar_wait(a_empty(a_st), a_par ^ 1, 1));
             if (elect_one()) {
-              mbar_arrive_expect_tx(a_full(a_st), (uint32_t)p.a_tx_bytes);
-              tma_load_4d(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+              if (CG == 2) {
+                if (rank == 0) mbar_arrive_expect_tx(a_full(a_st), 2u * (uint32_t)p.a_tx_bytes);
+                tma_load_4d_2sm(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+              } else {
+                mbar_arrive_expect_tx(a_full(a_st), (uint32_t)p.a_tx_bytes);
+                tma_load_4d(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+              }
             }
             __syncwarp();
             if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
@@ -154,8 +171,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               // one TMA box carries the weight tiles of `tgroup` consecutive taps: (32 ch, block_n, tgroup, 1)
               VT_TWAIT(1, mbar_wait(b_empty(b_st), b_par ^ 1, 3));
               if (elect_one()) {
-                mbar_arrive_expect_tx(b_full(b_st), (uint32_t)p.b_tx_bytes);
-                tma_load_4d(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), p.coff[s] + c0, n0, p.step_w[j], wb);
+                if (CG == 2) {   // this CTA stages rows [rank*block_n/2, +block_n/2) of the weight tile
+                  if (rank == 0) mbar_arrive_expect_tx(b_full(b_st), 2u * (uint32_t)p.b_tx_bytes);
+                  tma_load_4d_2sm(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), p.coff[s] + c0,
+                                  n0 + (int)rank * (p.block_n / 2), p.step_w[j], wb);
+                } else {
+                  mbar_arrive_expect_tx(b_full(b_st), (uint32_t)p.b_tx_bytes);
+                  tma_load_4d(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), p.coff[s] + c0, n0, p.step_w[j], wb);
+                }
               }
               __syncwarp();
               if (++b_st == p.b_stages) { b_st = 0; b_par ^= 1; }
@@ -165,13 +188,13 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer (whole warp converged; one elected lane issues) =================
-    const uint32_t idesc = make_idesc_tf32(TILE_M, p.block_n);
+  } else if (warp == 1 && rank == 0) {
+    // ================= MMA issuer (whole warp converged; one elected lane issues; CTA rank 0 only) =================
+    const uint32_t idesc = make_idesc_tf32(TILE_M * CG, p.block_n);
     int a_st = 0, b_st = 0, as = 0;
     uint32_t a_par = 0, b_par = 0, t_par = 0;
-    const uint32_t tile_bytes_n = (uint32_t)p.block_n * 128u;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const uint32_t tile_bytes_n = (uint32_t)(p.block_n / CG) * 128u;   // bytes of one tap's weight rows held by this CTA
+    for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
       VT_TWAIT(2, mbar_wait(t_empty(as), t_par ^ 1, 4));
       tc_fence_after();
       const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * p.mt * p.block_n);
@@ -205,13 +228,20 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               for (int g = 0; g < p.mt; ++g) {
                 const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)(g * TILE_W * 128), sbo, 0);
                 const uint32_t d_tmem = d_tmem0 + (uint32_t)(g * p.block_n);
-                umma_tf32(d_tmem, adesc, bdesc, idesc, first ^ 1u);
-                umma_tf32(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                umma_tf32(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                umma_tf32(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                if (CG == 2) {
+                  umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                  umma_tf32_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                  umma_tf32_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                  umma_tf32_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                } else {
+                  umma_tf32(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                  umma_tf32(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                  umma_tf32(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                  umma_tf32(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                }
               }
-              if (last_of_group) umma_commit(b_empty(b_st));
-              if (!p.halo) umma_commit(a_empty(a_st));
+              if (last_of_group) { if (CG == 2) umma_commit_2sm(b_empty(b_st)); else umma_commit(b_empty(b_st)); }
+              if (!p.halo) { if (CG == 2) umma_commit_2sm(a_empty(a_st)); else umma_commit(a_empty(a_st)); }
             }
             __syncwarp();
             first = 0;
@@ -219,13 +249,13 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             if (!p.halo) { if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; } }
           }
           if (p.halo) {
-            if (elect_one()) umma_commit(a_empty(a_st));
+            if (elect_one()) { if (CG == 2) umma_commit_2sm(a_empty(a_st)); else umma_commit(a_empty(a_st)); }
             __syncwarp();
             if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
           }
         }
       }
-      if (elect_one()) umma_commit(t_full(as));
+      if (elect_one()) { if (CG == 2) umma_commit_2sm(t_full(as)); else umma_commit(t_full(as)); }
       __syncwarp();
       if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
@@ -240,10 +270,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     const int nchunks = p.block_n / 32;
     int as = 0;
     uint32_t t_par = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
-      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w;
+      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
       VT_TWAIT(0, mbar_wait(t_full(as), t_par, 8));
       tc_fence_after();
@@ -253,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
         const bool in_img = oy < p.Ho && ox < p.Wo;
         const int64_t off0 = (int64_t)b * p.out_sb + (int64_t)oy * p.out_sy + (int64_t)ox * p.out_sx;
         const int64_t pix0 = (int64_t)b * p.pix_sb + (int64_t)oy * p.pix_sy + (int64_t)ox * p.pix_sx;   // dense-pixel index
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;   // fused ToRGB partial sums of this thread's pixel
         int ph = ph0, nb = nb0 - 32;
         for (int j = 0; j < nchunks; ++j, ++chunk) {
           // column -> (phase, channel): the N dimension is phase-major [n_phase][Cout]; a 32-column chunk never straddles
@@ -267,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             // every accumulator of this stage is in registers: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty(as));
+            if (lane == 0) { if (CG == 2) mbar_arrive_cta0(t_empty(as)); else mbar_arrive(t_empty(as)); }
           }
           // straight-line math: the 32 bias values come in as 8 vector loads issued together (a per-element __ldg inside a
           // branchy loop serialised 32 L1 latencies: ~4k cycles per chunk, measured), and the activation is selected
@@ -315,6 +346,19 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           }
           if (p.dbg) tw[2] += clock64() - t_math0;
           const long long t_st0 = p.dbg ? clock64() : 0;
+          if (p.rgb_w) {
+            // 1x1 modulated conv to 3 channels on the values just produced (model/stylegan/model.py:384-385)
+            const float4* w0 = reinterpret_cast<const float4*>(p.rgb_w + ((int64_t)(p.wB > 1 ? b : 0) * 3) * p.Cout + nb);
+            const float4* w1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w0) + p.Cout);
+            const float4* w2 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w0) + 2 * p.Cout);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a0 = __ldg(w0 + i), a1 = __ldg(w1 + i), a2 = __ldg(w2 + i);
+              rgb0 = fmaf(v[4 * i], a0.x, rgb0); rgb0 = fmaf(v[4 * i + 1], a0.y, rgb0); rgb0 = fmaf(v[4 * i + 2], a0.z, rgb0); rgb0 = fmaf(v[4 * i + 3], a0.w, rgb0);
+              rgb1 = fmaf(v[4 * i], a1.x, rgb1); rgb1 = fmaf(v[4 * i + 1], a1.y, rgb1); rgb1 = fmaf(v[4 * i + 2], a1.z, rgb1); rgb1 = fmaf(v[4 * i + 3], a1.w, rgb1);
+              rgb2 = fmaf(v[4 * i], a2.x, rgb2); rgb2 = fmaf(v[4 * i + 1], a2.y, rgb2); rgb2 = fmaf(v[4 * i + 2], a2.z, rgb2); rgb2 = fmaf(v[4 * i + 3], a2.w, rgb2);
+            }
+          }
           const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
           if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
           named_bar_sync(1, 128);
@@ -334,6 +378,45 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           }
           if (p.dbg) tw[3] += clock64() - t_st0;
         }
+        if (p.rgb_w && in_img) {
+          // + bias + Upsample(skip): upfirdn2d(up=2, pad=(2,1), 4x4 kernel) touches exactly 2x2 skip pixels per output
+          // pixel (taps with (y-2+ky) even).  Branch-free: clamped addresses + validity masks so the 12 loads issue together.
+          float o[3] = {rgb0 + __ldg(p.rgb_bias), rgb1 + __ldg(p.rgb_bias + 1), rgb2 + __ldg(p.rgb_bias + 2)};
+          const int64_t HW = (int64_t)p.Ho * p.Wo;
+          if (p.rgb_skip) {
+            const int hs = p.Ho >> 1, ws = p.Wo >> 1;
+            const int ky0 = (oy - 2) & 1, kx0 = (ox - 2) & 1;
+            const int iy0 = (oy - 2 + ky0) >> 1, ix0 = (ox - 2 + kx0) >> 1;        // second tap is +1
+            const float my0 = iy0 >= 0 ? 1.f : 0.f, my1 = (iy0 + 1) < hs ? 1.f : 0.f;
+            const float mx0 = ix0 >= 0 ? 1.f : 0.f, mx1 = (ix0 + 1) < ws ? 1.f : 0.f;
+            const int cy0 = iy0 < 0 ? 0 : iy0, cy1 = (iy0 + 1) < hs ? iy0 + 1 : hs - 1;
+            const int cx0 = ix0 < 0 ? 0 : ix0, cx1 = (ix0 + 1) < ws ? ix0 + 1 : ws - 1;
+            // flipped-kernel weights of the 4 taps (ky in {ky0, ky0+2}, kx in {kx0, kx0+2})
+            const float* kk = p.rgb_skip_kernel;
+            const float w00 = __ldg(kk + (3 - ky0) * 4 + (3 - kx0)) * my0 * mx0;
+            const float w01 = __ldg(kk + (3 - ky0) * 4 + (1 - kx0)) * my0 * mx1;
+            const float w10 = __ldg(kk + (1 - ky0) * 4 + (3 - kx0)) * my1 * mx0;
+            const float w11 = __ldg(kk + (1 - ky0) * 4 + (1 - kx0)) * my1 * mx1;
+            float s00[3], s01[3], s10[3], s11[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float* sp = p.rgb_skip + ((int64_t)b * 3 + c) * (int64_t)hs * ws;
+              s00[c] = __ldg(sp + (int64_t)cy0 * ws + cx0); s01[c] = __ldg(sp + (int64_t)cy0 * ws + cx1);
+              s10[c] = __ldg(sp + (int64_t)cy1 * ws + cx0); s11[c] = __ldg(sp + (int64_t)cy1 * ws + cx1);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              // same accumulation order as the reference loop (ky outer, kx inner)
+              float u = s00[c] * w00;
+              u = fmaf(s01[c], w01, u);
+              u = fmaf(s10[c], w10, u);
+              u = fmaf(s11[c], w11, u);
+              o[c] += u;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p.rgb_out[((int64_t)b * 3 + c) * HW + (int64_t)oy * p.Wo + ox] = o[c];
+        }
       }
       if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
@@ -347,10 +430,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     o[1] = (unsigned long long)tw[0]; o[2] = (unsigned long long)tw[1]; o[3] = (unsigned long long)tw[2]; o[4] = (unsigned long long)tw[3];
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -394,6 +478,7 @@ int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
 int g_tc_mode = 1;  // 0: one TMA box per tap; 1: one halo box per K chunk + row-shifted descriptors
 int g_tc_mt = 0;    // 0: automatic M-tiles per work item; 1/2/4: forced
 unsigned long long* g_tc_dbg = nullptr;   // device buffer [148][16] set through vt_set_debug_buffer (tuning only)
+int g_tc_cg2 = 1;     // 1: use CTA pairs (cta_group::2, M = 256) for N-tile-256 stride-1 halo convolutions
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
@@ -411,6 +496,9 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
   VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
+  VT_SUP(!d->rgb_w || (d->n_phase == 1 && d->Cout <= 256 && (((uintptr_t)d->rgb_w & 15) == 0) &&
+                       d->out_sx == d->Cout && d->out_sy == (int64_t)d->Wo * d->Cout && (!d->rgb_skip || (d->Ho % 2 == 0 && d->Wo % 2 == 0))),
+         "conv_tc: fused ToRGB needs Cout <= 256, one phase, a dense output and even Ho/Wo for the skip");
   return 1;
 #undef VT_SUP
 }
@@ -421,6 +509,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
+  if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
   return -1;
 }
 
@@ -452,6 +541,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     }
   }
   a.dbg = g_tc_dbg;
+  a.rgb_w = d->rgb_w; a.rgb_bias = d->rgb_bias; a.rgb_skip = d->rgb_skip; a.rgb_skip_kernel = d->rgb_skip_kernel; a.rgb_out = d->rgb_out;
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;
 
@@ -506,8 +596,16 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
       if (ok) { tgroup = tg; break; }
     }
   }
+  // CTA pairs: N tile 256, stride-1 halo mode, one M tile per CTA, one tap per weight box
+  const int halo1_bytes = (TILE_W + (dxmax - dxmin)) * (TILE_H + (dymax - dymin)) * 128;
+  const int cg = (g_tc_cg2 && can_halo && bn == 256 && mt == 1 && tgroup == 1 && d->Wo > TILE_W &&
+                  halo1_bytes <= d->taps * TILE_M * 128 / 2 && halo1_bytes <= 96 * 1024) ? 2 : 1;
   a.tgroup = tgroup;
-  a.b_tx_bytes = bn * 128 * tgroup;
+  for (int t = 0; t < d->taps && t < 32; ++t) {
+    if (t % tgroup == 0) a.grp_first_mask |= 1 << t;
+    if (t % tgroup == tgroup - 1) a.grp_last_mask |= 1 << t;
+  }
+  a.b_tx_bytes = (bn / cg) * 128 * tgroup;
   for (;; mt /= 2) {
     const int halo_w = TILE_W * mt + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
     const int halo_bytes = halo_w * halo_h * 128;
@@ -518,9 +616,9 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
     // shared memory plan: A ring (halo boxes or per-tap tiles) + B ring (weight tiles) + 2 output staging buffers
     a.a_stage_bytes = (int)(vt_cdiv(a.a_tx_bytes, 1024) * 1024);
-    a.b_stage_bytes = bn * 128 * tgroup;
+    a.b_stage_bytes = (bn / cg) * 128 * tgroup;
     a.a_stages = a.halo ? 3 : 4;
-    a.b_stages = tgroup > 1 ? 4 : 6;
+    a.b_stages = tgroup > 1 ? 4 : (cg == 2 ? 8 : 6);
     while (a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed > MAX_SMEM) {
       if (a.b_stages > 3) --a.b_stages;
       else if (a.a_stages > 2) --a.a_stages;
@@ -541,7 +639,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.tmem_cols = tc;
   a.block_n = bn;
   a.n_tiles = n_eff / bn;
-  a.tiles_x = (int)vt_cdiv(d->Wo, TILE_W * mt);
+  a.tiles_x = (int)vt_cdiv(d->Wo, TILE_W * mt * cg);
   a.tiles_y = (int)vt_cdiv(d->Ho, TILE_H);
   const int64_t total = (int64_t)a.n_tiles * a.B * a.tiles_x * a.tiles_y;
   VT_CHECK(total < (1LL << 31), "conv_tc: too many tiles");
@@ -577,7 +675,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     const uint64_t wc = (uint64_t)d->w_cstride;
     const uint64_t dims[4] = {wc, (uint64_t)n_eff, (uint64_t)d->w_taps, (uint64_t)d->wB};
     const uint64_t str[3] = {wc * 4, (uint64_t)n_eff * wc * 4, (uint64_t)d->w_taps * n_eff * wc * 4};
-    const uint32_t box[4] = {KCH, (uint32_t)bn, (uint32_t)a.tgroup, 1};
+    const uint32_t box[4] = {KCH, (uint32_t)(bn / cg), (uint32_t)a.tgroup, 1};
     if (make_map4(&a.w_map, d->weight, dims, str, box, "weight")) return 1;
   }
   for (int ph = 0; ph < d->n_phase; ++ph) {
@@ -591,43 +689,70 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
   });
   VT_CHECK(attr_err == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-  int grid = vt_num_sms();
-  if (grid > a.total_tiles) grid = a.total_tiles;
-  conv_tc_kernel<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(a);
+  if (cg == 1) {
+    int grid = vt_num_sms();
+    if (grid > a.total_tiles) grid = a.total_tiles;
+    conv_tc_kernel<1><<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(a);
+  } else {
+    int pairs = vt_num_sms() / 2;
+    if (pairs > a.total_tiles) pairs = a.total_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VT_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, a));
+  }
   VT_LAUNCH_CHECK();
   return 0;
 }
 
 // ---- tcgen05 issue-rate microbenchmark (tuning aid, tests/ and tools/ only) -----------------------------------------
-// One CTA per SM issues `reps` x 4 MMAs (M=128, N, K=8) on zero-filled smem operands without any TMA traffic.
+// One CTA per SM issues `reps` x 4 MMAs (M=128, N, K=8) on zero-filled smem operands.
 // variant bit 0: alternate between two accumulators; bit 1: issue from a converged warp (elect.sync) instead of a
-// lane-0 branch; bit 2: commit + wait after every group of 4 MMAs (round-trip latency).
+// lane-0 branch; bit 2: commit + wait after every group of 4 MMAs (round-trip latency); bit 3: rotate the operands over
+// 3 different smem buffers (defeats any operand reuse); bit 4: halo-style A descriptor (row-shifted start, SBO 1280);
+// bit 5: a second warp streams global->smem bulk copies (48 KB per round) concurrently (producer traffic).
 __global__ void __launch_bounds__(128, 1)
-tc_issue_bench_kernel(float* out, int N, int reps, int variant) {
+tc_issue_bench_kernel(float* out, const float* scratch, int N, int reps, int variant) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t OPB = 24576 + 32768;                       // one operand set: A (halo-sized) + B
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_addr = base, b_addr = base + 16384, bar = base + 16384 + 32768, slot = bar + 16;
+  const uint32_t bar = base + 3 * OPB, bar2 = bar + 8, slot = bar + 16, dump = base + 3 * OPB + 1024;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(gen)[i] = 0.f;
+  for (int i = threadIdx.x; i < (int)(3 * OPB / 4); i += blockDim.x) reinterpret_cast<float*>(gen)[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
   fence_proxy_async_smem();
   if (warp == 1) { tmem_alloc(slot, 512); tc_fence_before(); }
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
+  volatile int* stop = reinterpret_cast<volatile int*>(gen + (slot + 8 - base));
+  if (threadIdx.x == 0) *stop = 0;
+  __syncthreads();
   long long t0 = 0, t1 = 0;
   if (warp == 0) {
     const uint32_t idesc = make_idesc_tf32(128, N);
-    const uint64_t adesc = make_smem_desc_sw128(a_addr, 1024, 0), bdesc = make_smem_desc_sw128(b_addr, 1024, 0);
     uint32_t phase = 0;
     const bool converged = variant & 2;
     if (converged || lane == 0) {
       t0 = clock64();
       for (int r = 0; r < reps; ++r) {
+        const uint32_t ob = base + ((variant & 8) ? (uint32_t)(r % 3) * OPB : 0u);
+        const uint64_t adesc = (variant & 16) ? make_smem_desc_sw128(ob + (uint32_t)((r % 3) * 10 + (r % 2)) * 128u, 1280, 0)
+                                              : make_smem_desc_sw128(ob, 1024, 0);
+        const uint64_t bdesc = make_smem_desc_sw128(ob + 24576, 1024, 0);
         const uint32_t d = tmem + ((variant & 1) ? (uint32_t)((r & 1) * N) : 0u);
         if (converged) {
           if (elect_one()) {
@@ -651,18 +776,36 @@ tc_issue_bench_kernel(float* out, int N, int reps, int variant) {
       }
       t1 = clock64();
     }
+    if (lane == 0) *stop = 1;
     if (lane == 0 && blockIdx.x == 0) { out[0] = (float)(t1 - t0) / (float)(reps * 4); }
+  } else if (warp == 2 && (variant & 32)) {
+    // producer-like traffic: 1-D bulk copies global -> smem into a dump buffer, back to back
+    if (lane == 0) {
+      uint32_t ph = 0;
+      const float* src = scratch + (size_t)blockIdx.x * 12288;
+      long long bytes = 0;
+      while (!*stop) {
+        mbar_arrive_expect_tx(bar2, 49152);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dump), "l"(src), "r"(49152), "r"(bar2) : "memory");
+        mbar_wait(bar2, ph, 97);
+        ph ^= 1;
+        bytes += 49152;
+      }
+      if (blockIdx.x == 0) out[1] = (float)bytes;
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-extern "C" int vt_selftest_tc_gemm(const float*, const float*, float* D, int, int N, int K, int variant, void* stream) {
-  VT_CHECK(D && N >= 16 && N <= 256 && N % 16 == 0 && K >= 1, "selftest_tc_gemm: D (device float[1]) / N / reps invalid");
-  const int smem = 16384 + 32768 + 1024 + 1024;
+extern "C" int vt_selftest_tc_gemm(const float* A, const float*, float* D, int, int N, int K, int variant, void* stream) {
+  VT_CHECK(D && N >= 16 && N <= 256 && N % 16 == 0 && K >= 1, "selftest_tc_gemm: D (device float[2]) / N / reps invalid");
+  VT_CHECK(!(variant & 32) || A, "selftest_tc_gemm: variant bit 5 needs a scratch buffer A of 148*48 KB");
+  const int smem = 3 * (24576 + 32768) + 1024 + 49152 + 1024;
   VT_CUDA(cudaFuncSetAttribute(tc_issue_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc_issue_bench_kernel<<<vt_num_sms(), 128, smem, (cudaStream_t)stream>>>(D, N, K, variant);
+  tc_issue_bench_kernel<<<vt_num_sms(), 128, smem, (cudaStream_t)stream>>>(D, A, N, K, variant);
   VT_LAUNCH_CHECK();
   return 0;
 }

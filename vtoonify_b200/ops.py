@@ -32,7 +32,7 @@ def get_precision() -> str:
 
 
 # algorithm switches (kept so tests can compare both formulations on the GPU)
-_options = {"fold_upconv": True}
+_options = {"fold_upconv": True, "fuse_torgb": True}
 
 
 def set_option(name: str, value) -> None:
@@ -219,7 +219,7 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                 noise_w: Optional[torch.Tensor] = None, act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0,
                 res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
-                precision: Optional[str] = None) -> torch.Tensor:
+                precision: Optional[str] = None, rgb: Optional[dict] = None) -> torch.Tensor:
     """General NHWC convolution (virtual channel-concat of ``srcs``).
 
     ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
@@ -276,6 +276,14 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
         d.res = res.data_ptr()
     d.alpha, d.beta = alpha, beta
     d.round_tf32 = _round_flag()
+    rgb_out = None
+    if rgb is not None:
+        # fused ToRGB tail: rgb = {"w": [wB,3,Cout], "bias": [3], "skip": [B,3,Ho/2,Wo/2] or None, "kernel": [4,4]}
+        _req_cuda(rgb["w"], rgb["bias"], rgb.get("skip"), rgb.get("kernel"))
+        rgb_out = torch.empty((B, 3, Ho, Wo), device=srcs[0].device, dtype=torch.float32)
+        d.rgb_w, d.rgb_bias, d.rgb_out = rgb["w"].data_ptr(), rgb["bias"].data_ptr(), rgb_out.data_ptr()
+        if rgb.get("skip") is not None:
+            d.rgb_skip, d.rgb_skip_kernel = rgb["skip"].contiguous().data_ptr(), rgb["kernel"].contiguous().data_ptr()
     lib = _lib.load()
     if prec == "tf32" and lib.vt_conv2d_tc_supported(d):
         if _tc_profile is not None:
@@ -291,7 +299,12 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
             check(lib.vt_conv2d_tc_tf32(d, _stream()))
     else:
         check(lib.vt_conv2d_direct_f32(d, _stream()))
-    return out
+    return out if rgb is None else (out, rgb_out)
+
+
+def rgb_fusable(Cout: int, precision: Optional[str] = None) -> bool:
+    """The ToRGB tail can ride in the conv epilogue when one N tile holds all channels (tensor-core path only)."""
+    return (precision or _precision) == "tf32" and Cout % 32 == 0 and Cout <= 256 and _options["fuse_torgb"]
 
 
 def conv_out_size(n: int, k: int, stride: int, padding: int, dilation: int) -> int:

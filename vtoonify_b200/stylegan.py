@@ -194,8 +194,9 @@ class ModulatedConv2d(nn.Module):
         return ops.prep_weights(W.detach(), s, self.scale, self.demodulate, cin_pad, round_tf32=round_tf32)
 
     def forward_nhwc(self, x, style, externalweight=None, bias=None, noise=None, noise_w=None, act=False,
-                     slope=0.2, gain=ops.SQRT2):
-        """x NHWC -> NHWC.  Optional fused StyledConv epilogue (noise, bias, leaky relu)."""
+                     slope=0.2, gain=ops.SQRT2, rgb=None):
+        """x NHWC -> NHWC.  Optional fused StyledConv epilogue (noise, bias, leaky relu) and fused ToRGB tail
+        (``rgb`` dict, plain 3x3 form only: returns ``(out, rgb_image)``)."""
         B, H, W, Cs = x.shape
         k = self.kernel_size
         a = ACT_LRELU if act else ACT_NONE
@@ -219,7 +220,7 @@ class ModulatedConv2d(nn.Module):
             return ops.conv2d_nhwc([xb], w, ops.conv_taps(k, 0), 2, Ho, Wo, bias=bias, noise=noise, noise_w=noise_w,
                                    act=a, slope=slope, gain=gain)
         return ops.conv2d_nhwc([x], w, ops.conv_taps(k, self.padding), 1, H, W, bias=bias, noise=noise,
-                               noise_w=noise_w, act=a, slope=slope, gain=gain)
+                               noise_w=noise_w, act=a, slope=slope, gain=gain, rgb=rgb)
 
     def forward(self, input, style, externalweight=None):
         C = input.shape[1]
@@ -276,7 +277,9 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward_nhwc(self, x, style, noise=None, externalweight=None, zero_noise=False):
+    def forward_nhwc(self, x, style, noise=None, externalweight=None, zero_noise=False, to_rgb=None):
+        """``to_rgb`` = (ToRGB module, its style, skip image or None): also returns the RGB image, computed in this
+        conv's epilogue when possible (the activation is then never re-read for the 1x1 ToRGB conv)."""
         B, H, W, _ = x.shape
         Ho, Wo = (2 * H, 2 * W) if self.conv.upsample else (H, W)
         if zero_noise:
@@ -285,9 +288,20 @@ class StyledConv(nn.Module):
             if noise is None:
                 noise = torch.empty((B, 1, Ho, Wo), device=x.device, dtype=torch.float32).normal_()
             noise = _planar_noise(noise, B, Ho, Wo)
-        return self.conv.forward_nhwc(x, style, externalweight, bias=self.activate.bias, noise=noise,
-                                      noise_w=None if noise is None else self.noise.weight, act=True,
-                                      slope=self.activate.negative_slope, gain=self.activate.scale)
+        kw = dict(bias=self.activate.bias, noise=noise, noise_w=None if noise is None else self.noise.weight, act=True,
+                  slope=self.activate.negative_slope, gain=self.activate.scale)
+        if to_rgb is None:
+            return self.conv.forward_nhwc(x, style, externalweight, **kw)
+        trgb, style_rgb, skip = to_rgb
+        Cout = self.conv.out_channel
+        fuse = (ops.rgb_fusable(Cout) and not self.conv.upsample and not self.conv.downsample and trgb.fusable_skip(skip, H, W))
+        if not fuse:
+            out = self.conv.forward_nhwc(x, style, externalweight, **kw)
+            return out, trgb.forward_nhwc(out, style_rgb, skip)
+        w_rgb = trgb.conv.modulated_weights(style_rgb, Cout, round_tf32=False)      # [B, 1, 3, Cout]
+        rgb = {"w": w_rgb, "bias": trgb.bias.view(3), "skip": skip,
+               "kernel": trgb.upsample.kernel if skip is not None else None}
+        return self.conv.forward_nhwc(x, style, externalweight, rgb=rgb, **kw)
 
     def forward(self, input, style, noise=None, externalweight=None):
         C = input.shape[1]
@@ -305,12 +319,17 @@ class ToRGB(nn.Module):
         self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
+    def fusable_skip(self, skip, H, W):
+        """True if ``upfirdn2d(skip)`` is the standard up=2 / 4x4 / pad (2,1) form the fused kernels implement."""
+        return skip is None or (hasattr(self, "upsample") and self.upsample.factor == 2
+                                and tuple(self.upsample.kernel.shape) == (4, 4) and tuple(self.upsample.pad) == (2, 1)
+                                and skip.shape[2] * 2 == H and skip.shape[3] * 2 == W)
+
     def forward_nhwc(self, x, style, skip=None, externalweight=None):
         """x NHWC -> planar NCHW [B,3,H,W] (+ fused skip upsample/add)."""
         B, H, W, Cs = x.shape
         w = self.conv.modulated_weights(style, Cs, externalweight, round_tf32=False)   # CUDA-core kernel: keep fp32
-        fuse = (skip is not None and self.upsample.factor == 2 and tuple(self.upsample.kernel.shape) == (4, 4)
-                and self.upsample.pad == (2, 1) and skip.shape[2] * 2 == H and skip.shape[3] * 2 == W)
+        fuse = skip is not None and self.fusable_skip(skip, H, W)
         out = ops.smalln_conv(x, w, [(0, 0, 0)], 3, B, H, W, bias=self.bias.view(3),
                               skip=skip if fuse else None, skip_kernel=self.upsample.kernel if fuse else None)
         if skip is not None and not fuse:
@@ -409,8 +428,7 @@ class Generator(nn.Module):
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
                                                         self.to_rgbs):
             out = conv1.forward_nhwc(out, latent[:, i], noise=noise1)
-            out = conv2.forward_nhwc(out, latent[:, i + 1], noise=noise2)
-            skip = to_rgb.forward_nhwc(out, latent[:, i + 2], skip)
+            out, skip = conv2.forward_nhwc(out, latent[:, i + 1], noise=noise2, to_rgb=(to_rgb, latent[:, i + 2], skip))
             i += 2
             if i > return_feature_ind:
                 return ops.nhwc_as_nchw_view(out), skip

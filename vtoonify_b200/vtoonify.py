@@ -251,8 +251,8 @@ class VToonify(nn.Module):
                     out = self.fusion_out[fi].forward_nhwc(out, x2=f_E)
                     skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip)
             out = conv1.forward_nhwc(out, adastyles[:, _index + 6], zero_noise=True)
-            out = conv2.forward_nhwc(out, adastyles[:, _index + 7], zero_noise=True)
-            skip = to_rgb.forward_nhwc(out, adastyles[:, _index + 8], skip)
+            out, skip = conv2.forward_nhwc(out, adastyles[:, _index + 7], zero_noise=True,
+                                           to_rgb=(to_rgb, adastyles[:, _index + 8], skip))
             _index += 2
 
         image = skip

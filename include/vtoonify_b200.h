@@ -65,7 +65,7 @@ int vt_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W,
 
 /* ---- a8: EqualLinear ---------------------------------------------------------------------- */
 /* out[r, o] = act( sum_i in[r,i] * (W[o,i]*w_scale) + bias[o]*b_scale ), act: 0 none, 1 lrelu(0.2)*sqrt2 (fused_lrelu),
- * 2 lrelu(0.2) (nn.LeakyReLU) */
+ * 2 lrelu(0.2) (nn.LeakyReLU), 3 relu, 4 sigmoid */
 int vt_linear_f32(const float* in, const float* weight, const float* bias, float* out, int rows, int in_dim,
                   int out_dim, float w_scale, float b_scale, int act, void* stream);
 
@@ -137,6 +137,7 @@ typedef struct vt_conv_desc {
   const float* rgb_skip;        /* planar [B,3,Ho/2,Wo/2] or NULL                                */
   const float* rgb_skip_kernel; /* [4,4]                                                         */
   float*       rgb_out;         /* planar [B,3,Ho,Wo]                                            */
+  const float* slope_vec;       /* optional [Cout] per-channel negative slopes (PReLU) used by VT_ACT_LRELU instead of `slope` */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */
@@ -199,6 +200,15 @@ int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, i
 /* out[b,p,c] = gamma[b,c] * (x - mean) * rstd + beta[b,c]; gamma_beta: [B, 2*Cs] (gamma then beta) */
 int vt_adain_apply_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
                         const float* stats, const float* gamma_beta, float* out, int round_tf32, void* stream);
+
+/* ---- pSp encoder helpers (model/encoder/encoders/helpers.py:56-119, psp_encoders.py:72-88) ---------------- */
+/* out[b,y,x,c] = x[b,y,x,c] * gate[b,c] + sc[b, y*sc_stride, x*sc_stride, c]   (SE gate + shortcut add; gate may be NULL = 1,
+ * sc: NHWC [B, Hs, Ws, C] with Hs >= (H-1)*sc_stride+1; MaxPool2d(1, stride) shortcut == strided sampling) */
+int vt_gate_shortcut_add_nhwc(const float* x, const float* gate, const float* sc, float* out, int B, int H, int W, int C,
+                              int Hs, int Ws, int sc_stride, int round_tf32, void* stream);
+/* out = bilinear_resize(x [B,h,w,C] -> [H,W], align_corners=True) + y [B,H,W,C]   (FPN _upsample_add) */
+int vt_bilinear_add_nhwc(const float* x, const float* y, float* out, int B, int h, int w, int H, int W, int C,
+                         int round_tf32, void* stream);
 
 /* ---- elementwise helpers ------------------------------------------------------------------ */
 /* out = a * scale_a + b * scale_b (b may be NULL) */

@@ -256,3 +256,50 @@ def tensor2frame_u8(img, swap_rb=True):
     """clamp(-1,1) (style_transfer.py:177) then util.tensor2cv2: ((x+1)*127.5).astype(uint8), RGB->BGR."""
     t = ((img.clamp(-1, 1).permute(0, 2, 3, 1) + 1.0) * 127.5).to(torch.uint8)  # truncation like numpy astype
     return t.flip(-1) if swap_rb else t
+
+
+# ------------------------------------------------------------------------------------------------
+# a10: pSp GradualStyleEncoder (IR-SE-50)   (model/encoder/encoders/psp_encoders.py:35-116, helpers.py:56-119)
+# ------------------------------------------------------------------------------------------------
+def _bn(x, sd, p):
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5)
+
+
+def psp_forward(sd, x, n_styles=18):
+    """GradualStyleEncoder(50, 'ir_se').forward in eval mode, driven by its state_dict."""
+    h = F.prelu(_bn(F.conv2d(x, sd["input_layer.0.weight"], padding=1), sd, "input_layer.1."), sd["input_layer.2.weight"])
+    feats = {}
+    n_units = len({k.split(".")[1] for k in sd if k.startswith("body.")})
+    for i in range(n_units):
+        p = f"body.{i}."
+        w2 = sd[p + "res_layer.3.weight"]
+        has_sc_conv = (p + "shortcut_layer.0.weight") in sd
+        # the first unit of every stage has stride 2 (helpers.py:25-26): unit 0 (64->64, MaxPool2d(1,2) shortcut) and the
+        # units whose depth changes (conv shortcut)
+        stride = 2 if (has_sc_conv or i == 0) else 1
+        if has_sc_conv:
+            sc = _bn(F.conv2d(h, sd[p + "shortcut_layer.0.weight"], stride=stride), sd, p + "shortcut_layer.1.")
+        else:
+            sc = F.max_pool2d(h, 1, stride)
+        t = _bn(h, sd, p + "res_layer.0.")
+        t = F.prelu(F.conv2d(t, sd[p + "res_layer.1.weight"], padding=1), sd[p + "res_layer.2.weight"])
+        t = _bn(F.conv2d(t, w2, stride=stride, padding=1), sd, p + "res_layer.4.")
+        g = F.adaptive_avg_pool2d(t, 1)
+        g = torch.sigmoid(F.conv2d(F.relu(F.conv2d(g, sd[p + "res_layer.5.fc1.weight"])), sd[p + "res_layer.5.fc2.weight"]))
+        h = t * g + sc
+        feats[i] = h
+    c1, c2, c3 = feats[6], feats[20], feats[23]
+
+    def head(j, f):
+        t, k = f, 0
+        while f"styles.{j}.convs.{k}.weight" in sd:
+            t = F.leaky_relu(F.conv2d(t, sd[f"styles.{j}.convs.{k}.weight"], sd[f"styles.{j}.convs.{k}.bias"], stride=2, padding=1), 0.01)
+            k += 2
+        return equal_linear(t.view(-1, 512), sd[f"styles.{j}.linear.weight"], sd[f"styles.{j}.linear.bias"])
+
+    lat = [head(j, c3) for j in range(3)]
+    p2 = F.interpolate(c3, size=c2.shape[2:], mode="bilinear", align_corners=True) + F.conv2d(c2, sd["latlayer1.weight"], sd["latlayer1.bias"])
+    lat += [head(j, p2) for j in range(3, 7)]
+    p1 = F.interpolate(p2, size=c1.shape[2:], mode="bilinear", align_corners=True) + F.conv2d(c1, sd["latlayer2.weight"], sd["latlayer2.bias"])
+    lat += [head(j, p1) for j in range(7, n_styles)]
+    return torch.stack(lat, dim=1)

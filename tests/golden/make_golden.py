@@ -177,8 +177,23 @@ def golden_generator():
     print("generator32 rms %.3f" % img.pow(2).mean().sqrt())
 
 
+def golden_psp():
+    from argparse import Namespace
+    from model.encoder.encoders.psp_encoders import GradualStyleEncoder
+    m = GradualStyleEncoder(50, "ir_se", Namespace(input_nc=3, n_styles=18)).eval()
+    keys = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_keys_psp.json"), "w") as f:
+        json.dump(keys, f, indent=0)
+    m.load_state_dict(det_state_dict(m, seed=11), strict=True)
+    x = (torch.rand((1, 3, 256, 256), generator=gen(21)) * 2 - 1).half().float()   # stored as fp16, exactly reproducible
+    y = m(x)
+    print("psp", tuple(y.shape), "rms %.3f" % y.pow(2).mean().sqrt())
+    save("psp", x=x.half(), y=y)
+
+
 if __name__ == "__main__":
     golden_ops()
     golden_layers()
     golden_generator()
     golden_vtoonify()
+    golden_psp()

@@ -114,3 +114,15 @@ def test_ops_reject_cpu_tensors_without_gpu():
         ops.fused_bias_act(torch.zeros(1, 2, 3, 3), None, 0.2, 1.0)
     with pytest.raises(_lib.VtError):
         ops.to_nhwc(torch.zeros(1, 2, 3, 3))
+
+
+def test_psp_state_dict_contract():
+    """a10: GradualStyleEncoder(50, 'ir_se') has the reference's 621 keys/shapes (load_psp_standalone loads it strict)."""
+    from argparse import Namespace
+    from vtoonify_b200.psp import GradualStyleEncoder, get_blocks
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys_psp.json")))
+    sd = GradualStyleEncoder(50, "ir_se", Namespace(input_nc=3, n_styles=18)).state_dict()
+    assert list(sd.keys()) == list(keys.keys()) and len(sd) == 621
+    assert all(list(sd[k].shape) == keys[k] for k in keys)
+    cfg = get_blocks(50)
+    assert len(cfg) == 24 and [i for i, c in enumerate(cfg) if c[2] == 2] == [0, 3, 7, 21]

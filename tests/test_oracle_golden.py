@@ -120,3 +120,14 @@ def test_frame_transforms():
     c = np.clip(img.numpy(), -1, 1).transpose(0, 2, 3, 1)
     ref8 = ((c + 1.0) * 127.5).astype(np.uint8)[..., ::-1]
     assert np.array_equal(out, ref8)
+
+
+def test_psp_encoder_golden(golden):
+    """a10: pSp GradualStyleEncoder(50, 'ir_se') restated functionally vs the reference module's output."""
+    g = golden("psp")
+    keys = json.load(open("tests/golden/state_dict_keys_psp.json"))
+    sd = det_state_dict({k: torch.empty(v, dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+                         for k, v in keys.items()}, seed=11)
+    y = O.psp_forward(sd, T(g["x"]).float())
+    ref = T(g["y"])
+    assert_close(y, ref, 1e-4 * ref.abs().max().item(), "pSp encoder")

@@ -22,5 +22,6 @@ run conv_tc_pairs 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "c
 run conv_tc_fold 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "folded"
 run layers 900 python -m pytest tests/test_gpu_layers.py -q -m gpu -s
 run vtoonify 900 python -m pytest tests/test_gpu_vtoonify.py -q -m gpu -s
+run psp 600 python -m pytest tests/test_gpu_psp.py -q -m gpu -s
 run smoke 600 python -c "import __graft_entry__ as g; g.smoke()"
 cat gpurun_out/summary.txt

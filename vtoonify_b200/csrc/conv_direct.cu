@@ -108,7 +108,7 @@ conv_direct_kernel(const __grid_constant__ DirectArgs args) {
       float v = acc[i][j];
       if (d.noise) v += nz;
       if (d.bias) v += d.bias[n];
-      if (d.act == VT_ACT_LRELU) v = vt_lrelu(v, d.slope) * d.gain;
+      if (d.act == VT_ACT_LRELU) v = vt_lrelu(v, d.slope_vec ? d.slope_vec[n] : d.slope) * d.gain;
       else if (d.act == VT_ACT_RELU_TANH) v = tanhf(fmaxf(v, 0.f));
       if (d.res) v = v * d.alpha + d.beta * d.res[off + n];
       else if (d.alpha != 1.f) v = v * d.alpha;

@@ -63,6 +63,7 @@ struct TcArgs {
   unsigned long long* dbg;   // optional [grid][16] cycle counters (tuning only)
   // fused ToRGB tail
   const float* rgb_w; const float* rgb_bias; const float* rgb_skip; const float* rgb_skip_kernel; float* rgb_out;
+  const float* slope_vec;
 };
 
 #define VT_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
@@ -318,8 +319,20 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             for (int i = 0; i < 32; ++i) v[i] += nz;
           }
           if (p.act == VT_ACT_LRELU) {
+            if (p.slope_vec) {   // PReLU: per-channel negative slope
+              const float4* sp = reinterpret_cast<const float4*>(p.slope_vec + nb);
+              float4 sq[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = vt_lrelu(v[i], p.slope) * p.gain;
+              for (int i = 0; i < 8; ++i) sq[i] = __ldg(sp + i);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[4 * i + 0] = vt_lrelu(v[4 * i + 0], sq[i].x) * p.gain; v[4 * i + 1] = vt_lrelu(v[4 * i + 1], sq[i].y) * p.gain;
+                v[4 * i + 2] = vt_lrelu(v[4 * i + 2], sq[i].z) * p.gain; v[4 * i + 3] = vt_lrelu(v[4 * i + 3], sq[i].w) * p.gain;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = vt_lrelu(v[i], p.slope) * p.gain;
+            }
           } else if (p.act == VT_ACT_RELU_TANH) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = tanhf(fmaxf(v[i], 0.f));
@@ -496,6 +509,7 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
   VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
+  VT_SUP(!d->slope_vec || (((uintptr_t)d->slope_vec & 15) == 0), "conv_tc: slope_vec not 16-byte aligned");
   VT_SUP(!d->rgb_w || (d->n_phase == 1 && d->Cout <= 256 && (((uintptr_t)d->rgb_w & 15) == 0) &&
                        d->out_sx == d->Cout && d->out_sy == (int64_t)d->Wo * d->Cout && (!d->rgb_skip || (d->Ho % 2 == 0 && d->Wo % 2 == 0))),
          "conv_tc: fused ToRGB needs Cout <= 256, one phase, a dense output and even Ho/Wo for the skip");
@@ -541,6 +555,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     }
   }
   a.dbg = g_tc_dbg;
+  a.slope_vec = d->slope_vec;
   a.rgb_w = d->rgb_w; a.rgb_bias = d->rgb_bias; a.rgb_skip = d->rgb_skip; a.rgb_skip_kernel = d->rgb_skip_kernel; a.rgb_out = d->rgb_out;
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;

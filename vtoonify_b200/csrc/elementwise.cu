@@ -128,6 +128,63 @@ f32_to_frame_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, 
   }
 }
 
+// SE gate * x + (strided) shortcut, float4 over channels
+__global__ void __launch_bounds__(256)
+gate_shortcut_add_kernel(const float* __restrict__ x, const float* __restrict__ gate, const float* __restrict__ sc,
+                         float* __restrict__ out, int H, int W, int C, int Hs, int Ws, int sc_stride, int round_tf32) {
+  const int b = blockIdx.y;
+  const int nvec = C / 4;
+  const int64_t total = (int64_t)H * W * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 4;
+    const int64_t p = i / nvec;
+    const int xx = (int)(p % W), yy = (int)(p / W);
+    float4 v = *reinterpret_cast<const float4*>(x + (((int64_t)b * H + yy) * W + xx) * C + c);
+    if (gate) {
+      const float4 g = *reinterpret_cast<const float4*>(gate + (int64_t)b * C + c);
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    const float4 s = *reinterpret_cast<const float4*>(sc + (((int64_t)b * Hs + (int64_t)yy * sc_stride) * Ws + (int64_t)xx * sc_stride) * C + c);
+    v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+    if (round_tf32) { v.x = vt_round_tf32(v.x); v.y = vt_round_tf32(v.y); v.z = vt_round_tf32(v.z); v.w = vt_round_tf32(v.w); }
+    *reinterpret_cast<float4*>(out + (((int64_t)b * H + yy) * W + xx) * C + c) = v;
+  }
+}
+
+// F.interpolate(x, size=(H,W), mode='bilinear', align_corners=True) + y  (psp_encoders.py:87-88)
+__global__ void __launch_bounds__(256)
+bilinear_add_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int h, int w, int H,
+                    int W, int C, int round_tf32) {
+  const int b = blockIdx.y;
+  const int nvec = C / 4;
+  const int64_t total = (int64_t)H * W * nvec;
+  const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 4;
+    const int64_t p = i / nvec;
+    const int ox = (int)(p % W), oy = (int)(p / W);
+    const float fy = oy * sy, fx = ox * sx;
+    int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* xb = x + (int64_t)b * h * w * C + c;
+    const float4 v00 = *reinterpret_cast<const float4*>(xb + ((int64_t)y0 * w + x0) * C);
+    const float4 v01 = *reinterpret_cast<const float4*>(xb + ((int64_t)y0 * w + x1) * C);
+    const float4 v10 = *reinterpret_cast<const float4*>(xb + ((int64_t)y1 * w + x0) * C);
+    const float4 v11 = *reinterpret_cast<const float4*>(xb + ((int64_t)y1 * w + x1) * C);
+    const float4 yy = *reinterpret_cast<const float4*>(y + (((int64_t)b * H + oy) * W + ox) * C + c);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float4 o;
+    o.x = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x + yy.x;
+    o.y = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y + yy.y;
+    o.z = w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z + yy.z;
+    o.w = w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w + yy.w;
+    if (round_tf32) { o.x = vt_round_tf32(o.x); o.y = vt_round_tf32(o.y); o.z = vt_round_tf32(o.z); o.w = vt_round_tf32(o.w); }
+    *reinterpret_cast<float4*>(out + (((int64_t)b * H + oy) * W + ox) * C + c) = o;
+  }
+}
+
 inline unsigned grid_for(int64_t work_items, int threads) {
   int64_t blocks = vt_cdiv(work_items, threads);
   const int64_t cap = (int64_t)vt_num_sms() * 16;
@@ -183,6 +240,25 @@ extern "C" int vt_axpby_f32(const float* a, const float* b, float* out, int64_t 
   VT_CHECK(a && out && n >= 0, "axpby: bad args");
   if (n == 0) return 0;
   axpby_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, scale_a, scale_b, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_gate_shortcut_add_nhwc(const float* x, const float* gate, const float* sc, float* out, int B, int H, int W,
+                                         int C, int Hs, int Ws, int sc_stride, int round_tf32, void* stream) {
+  VT_CHECK(x && sc && out && B >= 1 && B <= 65535 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0, "gate_shortcut_add: bad args");
+  VT_CHECK(sc_stride >= 1 && (int64_t)(H - 1) * sc_stride < Hs && (int64_t)(W - 1) * sc_stride < Ws, "gate_shortcut_add: shortcut too small");
+  dim3 grid(grid_for((int64_t)H * W * (C / 4), 256), (unsigned)B);
+  gate_shortcut_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gate, sc, out, H, W, C, Hs, Ws, sc_stride, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vt_bilinear_add_nhwc(const float* x, const float* y, float* out, int B, int h, int w, int H, int W, int C,
+                                    int round_tf32, void* stream) {
+  VT_CHECK(x && y && out && B >= 1 && B <= 65535 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0, "bilinear_add: bad args");
+  dim3 grid(grid_for((int64_t)H * W * (C / 4), 256), (unsigned)B);
+  bilinear_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, out, h, w, H, W, C, round_tf32);
   VT_LAUNCH_CHECK();
   return 0;
 }

@@ -29,6 +29,8 @@ linear_kernel(const float* __restrict__ in, const float* __restrict__ weight, co
     const float b = bias ? bias[o] * b_scale : 0.f;
     if (act == 1) v = vt_lrelu(v + b, 0.2f) * 1.4142135623730951f;
     else if (act == 2) v = vt_lrelu(v + b, 0.2f);
+    else if (act == 3) v = fmaxf(v + b, 0.f);
+    else if (act == 4) v = 1.0f / (1.0f + expf(-(v + b)));
     else v = v + b;
     out[(int64_t)r * out_dim + o] = v;
   }
@@ -153,7 +155,7 @@ extern "C" int vt_fold_upconv_weights_f32(const float* w, const float* blur, flo
 extern "C" int vt_linear_f32(const float* in, const float* weight, const float* bias, float* out, int rows, int in_dim,
                              int out_dim, float w_scale, float b_scale, int act, void* stream) {
   VT_CHECK(in && weight && out && rows >= 1 && in_dim >= 1 && out_dim >= 1, "linear: bad args");
-  VT_CHECK(act >= 0 && act <= 2, "linear: act must be 0, 1 or 2");
+  VT_CHECK(act >= 0 && act <= 4, "linear: act must be in [0, 4]");
   const int64_t warps = (int64_t)rows * out_dim;
   const int threads = 256;
   const int64_t blocks = vt_cdiv(warps * 32, threads);

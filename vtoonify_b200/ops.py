@@ -219,7 +219,8 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                 noise_w: Optional[torch.Tensor] = None, act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0,
                 res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
-                precision: Optional[str] = None, rgb: Optional[dict] = None) -> torch.Tensor:
+                precision: Optional[str] = None, rgb: Optional[dict] = None,
+                slope_vec: Optional[torch.Tensor] = None) -> torch.Tensor:
     """General NHWC convolution (virtual channel-concat of ``srcs``).
 
     ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
@@ -270,6 +271,9 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     d.noise = _ptr(noise)
     d.noise_w = _ptr(noise_w)
     d.act, d.slope, d.gain = act, slope, gain
+    if slope_vec is not None:
+        _req_cuda(slope_vec)
+        d.slope_vec = slope_vec.contiguous().data_ptr()
     if res is not None:
         if out_view is not None or res.shape != (B, Ho, Wo, Cout) or not res.is_contiguous():
             raise _lib.VtError("conv2d_nhwc: residual must match a dense output")
@@ -471,6 +475,26 @@ def affine_fold_weights(w: torch.Tensor, stats: torch.Tensor, gamma_beta: torch.
     check(_lib.load().vt_affine_fold_weights_f32(w.data_ptr(), stats.data_ptr(), gamma_beta.contiguous().data_ptr(),
                                                  out_w.data_ptr(), out_k.data_ptr(), B, taps * N, C2, _stream()))
     return out_w, out_k
+
+
+def gate_shortcut_add(x: torch.Tensor, gate: Optional[torch.Tensor], sc: torch.Tensor, sc_stride: int = 1) -> torch.Tensor:
+    """``x * gate[b,c] + sc[b, y*s, x*s, c]`` (SE gate and residual shortcut; a MaxPool2d(1, s) shortcut is the strided read)."""
+    _req_cuda(x, gate, sc)
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    check(_lib.load().vt_gate_shortcut_add_nhwc(x.data_ptr(), _ptr(None if gate is None else gate.contiguous()), sc.data_ptr(),
+                                                out.data_ptr(), B, H, W, C, sc.shape[1], sc.shape[2], sc_stride, _round_flag(), _stream()))
+    return out
+
+
+def bilinear_add(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """``F.interpolate(x, size=y.shape[1:3], mode='bilinear', align_corners=True) + y`` on NHWC tensors."""
+    _req_cuda(x, y)
+    B, h, w, C = x.shape
+    _, H, W, _ = y.shape
+    out = torch.empty_like(y)
+    check(_lib.load().vt_bilinear_add_nhwc(x.data_ptr(), y.data_ptr(), out.data_ptr(), B, h, w, H, W, C, _round_flag(), _stream()))
+    return out
 
 
 def axpby(a: torch.Tensor, b: Optional[torch.Tensor], sa: float, sb: float = 0.0, round_tf32: Optional[bool] = None) -> torch.Tensor:

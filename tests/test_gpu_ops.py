@@ -202,3 +202,38 @@ def test_adain_vs_oracle():
     ref2 = gb2[:, :128, None, None] * F.instance_norm(cat, eps=1e-5) + gb2[:, 128:, None, None]
     assert maxerr(y2, ref2) <= 2e-5
     ops.set_precision("tf32")
+
+
+def test_upfirdn2d_tiled_and_generic_kernels_agree():
+    """The shared-memory tiled kernel and the generic kernel implement the same index semantics (random configs incl.
+    larger planes, negative pads, up/down up to 3) and both match the oracle."""
+    from vtoonify_b200 import _lib
+    from vtoonify_b200.op import upfirdn2d
+    lib = _lib.load()
+    rng = np.random.RandomState(7)
+    g = torch.Generator().manual_seed(7)
+    n = 0
+    while n < 40:
+        H, W = int(rng.randint(1, 90)), int(rng.randint(1, 300))
+        kh, kw = int(rng.randint(1, 7)), int(rng.randint(1, 7))
+        up = (int(rng.randint(1, 4)), int(rng.randint(1, 4)))
+        down = (int(rng.randint(1, 4)), int(rng.randint(1, 4)))
+        pad = tuple(int(v) for v in rng.randint(-2, 5, size=4))
+        oh = (H * up[1] + pad[2] + pad[3] - kh + down[1]) // down[1]
+        ow = (W * up[0] + pad[0] + pad[1] - kw + down[0]) // down[0]
+        if oh < 1 or ow < 1 or H * up[1] + min(pad[2], 0) + min(pad[3], 0) < 1 or W * up[0] + min(pad[0], 0) + min(pad[1], 0) < 1:
+            continue
+        x = torch.randn((2, 3, H, W), generator=g)
+        k = torch.randn((kh, kw), generator=g)
+        ref = O.upfirdn2d(x, k, up, down, pad)
+        outs = []
+        for tiled in (1, 0):
+            old = lib.vt_set_option(b"upfirdn_tiled", tiled)
+            try:
+                outs.append(upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad).cpu())
+            finally:
+                lib.vt_set_option(b"upfirdn_tiled", old)
+        for y in outs:
+            assert y.shape == ref.shape, (H, W, kh, kw, up, down, pad)
+            assert maxerr(y, ref) <= 2e-5 * max(1.0, ref.abs().max().item()), (H, W, kh, kw, up, down, pad, maxerr(y, ref))
+        n += 1

@@ -26,6 +26,7 @@
 using namespace vt_tc;
 
 int vt_validate_conv_desc(const vt_conv_desc* d, const char* who);
+extern int g_upfirdn_tiled;
 
 namespace {
 
@@ -524,6 +525,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
+  if (key && strcmp(key, "upfirdn_tiled") == 0) { int old = g_upfirdn_tiled; g_upfirdn_tiled = value; return old; }
   return -1;
 }
 

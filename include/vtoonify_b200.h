@@ -87,6 +87,10 @@ int vt_modulate_weights_f32(const float* W, const float* style, float* out, int 
 int vt_fold_upconv_weights_f32(const float* w, const float* blur, float* out, int wB, int Cout, int cpad, int round_tf32,
                                void* stream);
 
+/* Split fp32 weight rows for the bf16x3 tensor-core mode: for every 32-channel chunk (128 bytes) of every row,
+ * out = [bf16(w) x 32 | bf16(w - bf16(w)) x 32] (128 bytes). w, out: [rows][C] fp32-sized elements, C % 32 == 0. */
+int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, void* stream);
+
 /* ---- convolution descriptor (NHWC activations) -------------------------------------------- */
 #define VT_MAX_TAPS 36     /* 9 taps x up to 4 output phases (folded up-conv) */
 #define VT_ACT_NONE 0
@@ -138,6 +142,9 @@ typedef struct vt_conv_desc {
   const float* rgb_skip_kernel; /* [4,4]                                                         */
   float*       rgb_out;         /* planar [B,3,Ho,Wo]                                            */
   const float* slope_vec;       /* optional [Cout] per-channel negative slopes (PReLU) used by VT_ACT_LRELU instead of `slope` */
+  const void*  weight_bf16x3;   /* optional: `weight` split by vt_split_weights_bf16x3 (same shape/strides in bytes). When set, the
+                                 * tensor-core kernel computes a*w as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with bf16 operands
+                                 * (fp32-class accuracy, 1.5x the MMA work of TF32); ignored by the direct kernel          */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */
@@ -146,7 +153,8 @@ int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream);
  * Cout % 16 == 0, 16B-aligned views. */
 int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream);
 int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 accepts the descriptor */
-/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","upfirdn_tiled"}; returns previous value */
+/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","upfirdn_tiled"};
+ * returns the previous value (-1 for an unknown key) */
 int vt_set_option(const char* key, int value);
 /* tuning only: device buffer of 148*16 uint64 that conv_tc fills with per-role wait-cycle counters (NULL disables) */
 int vt_set_debug_buffer(void* dev_ptr);

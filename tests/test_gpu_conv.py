@@ -56,7 +56,7 @@ def test_direct_vs_torch(case):
     ref = F.conv2d(x, w, b, stride=stride, padding=pad, dilation=dil)
     y = _run(ops, x, w, b, k, stride, pad, dil, "fp32")
     assert maxerr(y, ref) <= 5e-5, maxerr(y, ref)
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -75,7 +75,7 @@ def test_tc_vs_direct_exact_data(case, mode):
         y = _run(ops, x, w, b, k, stride, pad, dil, "tf32")
     finally:
         _lib.load().vt_set_option(b"tc_mode", old)
-        ops.set_precision("tf32")
+        ops.set_precision(ops.DEFAULT_PRECISION)
     scale = ref.abs().max().item()
     assert maxerr(y, ref) <= 2e-5 * max(1.0, scale), f"mode {mode}: err {maxerr(y, ref):.3e} (scale {scale:.1f})"
 
@@ -94,7 +94,7 @@ def test_tc_epilogue_variants():
         y = _run(ops, x, w, b, 3, 1, 1, 1, prec, noise=noise.cuda(), noise_w=nw.cuda(), act=_lib.ACT_LRELU, slope=0.2,
                  gain=1.5, res=ops.to_nhwc(res.cuda(), round_tf32=False), alpha=0.7, beta=0.3)
         assert maxerr(y, ref) <= 1e-4, (prec, maxerr(y, ref))
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 def test_virtual_concat_two_sources():
@@ -109,7 +109,7 @@ def test_virtual_concat_two_sources():
         y = ops.conv2d_nhwc([ops.to_nhwc(a.cuda(), round_tf32=False), ops.to_nhwc(c.cuda(), round_tf32=False)], wp,
                             ops.conv_taps(3, 1), 1, 10, 9, precision=prec)
         assert maxerr(ops.to_nchw(y).cpu(), ref) <= 1e-4, prec
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
@@ -121,7 +121,7 @@ def test_conv_transpose_polyphase(prec):
     ops.set_precision("fp32")
     wp = ops.prep_weights(w.cuda(), cin_pad=64)
     y = ops.conv_transpose2d_s2_k3_nhwc(ops.to_nhwc(x.cuda(), round_tf32=False), wp, precision=prec)
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
     assert y.shape == (2, 15, 19, 32)
     assert maxerr(ops.to_nchw(y).cpu(), ref) <= 1e-4
 
@@ -138,6 +138,7 @@ def test_tf32_random_data_error_budget():
     err = maxerr(ops.to_nchw(y).cpu(), ref)
     rms = ref.pow(2).mean().sqrt().item()
     print(f"tf32 conv 256->256: max err {err:.3e}, rms {rms:.3f}, rel {err / rms:.3e}")
+    ops.set_precision(ops.DEFAULT_PRECISION)
     assert err <= 4e-3 * rms
 
 
@@ -171,7 +172,7 @@ def test_smalln_conv_variants():
     y2 = ops.smalln_conv(xn, ops.prep_weights(w2.cuda(), cin_pad=C), [(0, 0, 0)], 3, B, H, W, bias=b.cuda(),
                          skip=sk.cuda(), skip_kernel=k4.cuda())
     assert maxerr(y2.cpu(), ref2) <= 2e-5
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 @pytest.mark.parametrize("mt", [1, 2, 4])
@@ -191,7 +192,7 @@ def test_tc_m_tiles_per_work_item(case, mt):
         y = _run(ops, x, w, b, k, stride, pad, dil, "tf32")
     finally:
         _lib.load().vt_set_option(b"tc_mt", old)
-        ops.set_precision("tf32")
+        ops.set_precision(ops.DEFAULT_PRECISION)
     scale = ref.abs().max().item()
     assert maxerr(y, ref) <= 2e-5 * max(1.0, scale), f"mt {mt}: err {maxerr(y, ref):.3e} (scale {scale:.1f})"
 
@@ -221,14 +222,14 @@ def test_folded_upconv(shape):
     ops.set_precision("fp32")   # no output rounding in either run
     a = ops.conv_up2_folded_nhwc(xn, wfr, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135, precision="fp32")
     t = ops.conv_up2_folded_nhwc(xn, wfr, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135, precision="tf32")
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
     assert maxerr(ops.to_nchw(t).cpu(), ops.to_nchw(a).cpu()) <= 2e-5 * max(1.0, ref.abs().max().item())
     assert maxerr(ops.to_nchw(t).cpu(), ref) <= 5e-3 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("cg2", [0, 1])
-@pytest.mark.parametrize("case", [CASES[3], CASES[4], (2, 256, 256, 40, 24, 3, 1, 1, 1), (1, 512, 512, 16, 16, 3, 1, 4, 4),
-                                  (2, 64, 256, 17, 9, 3, 1, 1, 1)])
+@pytest.mark.parametrize("cg2", [0, 1, 2])
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], (2, 256, 256, 40, 24, 3, 1, 1, 1), (1, 512, 512, 16, 16, 3, 1, 4, 4),
+                                  (2, 64, 256, 17, 9, 3, 1, 1, 1), (2, 32, 32, 33, 70, 3, 1, 1, 1)])
 def test_tc_cta_pairs(case, cg2):
     """cta_group::2 (CTA pair, M = 256) vs single-CTA tcgen05 vs the FFMA kernel on N-tile-256 layers."""
     from vtoonify_b200 import _lib, ops
@@ -246,6 +247,139 @@ def test_tc_cta_pairs(case, cg2):
         y = _run(ops, x, w, b, k, stride, pad, dil, "tf32", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
     finally:
         _lib.load().vt_set_option(b"tc_cg2", old)
-        ops.set_precision("tf32")
+        ops.set_precision(ops.DEFAULT_PRECISION)
     scale = ref.abs().max().item()
     assert maxerr(y, ref) <= 2e-5 * max(1.0, scale), f"cg2 {cg2}: err {maxerr(y, ref):.3e} (scale {scale:.1f})"
+
+
+# ---- bf16x3: split-operand tensor-core mode on arbitrary fp32 data ------------------------------------------------------
+BF16X3_TOL = 3e-5     # max-abs error relative to max(1, |ref|max): three bf16 products drop only the a_lo*w_lo term (~2^-17)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", CASES + [(2, 256, 256, 40, 24, 3, 1, 1, 1)])
+def test_bf16x3_vs_direct_random_data(case, mode):
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007 + 1)
+    x = torch.randn((B, Cin, H, W), generator=g) * 3.0
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32")
+    old = _lib.load().vt_set_option(b"tc_mode", mode)
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "bf16x3")
+    finally:
+        _lib.load().vt_set_option(b"tc_mode", old)
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    scale = max(1.0, ref.abs().max().item())
+    err = maxerr(y, ref)
+    print(f"bf16x3 {case} mode {mode}: err {err:.3e} scale {scale:.2f}")
+    assert err <= BF16X3_TOL * scale
+
+
+@pytest.mark.parametrize("mt,cg2", [(1, 0), (1, 1), (2, 0), (4, 0)])
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[5], (2, 256, 256, 40, 24, 3, 1, 1, 1), (2, 64, 256, 17, 9, 3, 1, 1, 1)])
+def test_bf16x3_work_item_shapes(case, mt, cg2):
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007 + 2)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn((B, Cout, H, W), generator=g)
+    kw = dict(act=_lib.ACT_LRELU, slope=0.2, gain=1.25, alpha=0.5, beta=0.75)
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    lib = _lib.load()
+    old = (lib.vt_set_option(b"tc_mt", mt), lib.vt_set_option(b"tc_cg2", cg2))
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "bf16x3", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    finally:
+        lib.vt_set_option(b"tc_mt", old[0]); lib.vt_set_option(b"tc_cg2", old[1])
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    scale = max(1.0, ref.abs().max().item())
+    assert maxerr(y, ref) <= BF16X3_TOL * scale, f"mt {mt} cg2 {cg2}: {maxerr(y, ref):.3e} (scale {scale:.1f})"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 7, 9), (1, 128, 64, 16, 24), (1, 512, 256, 8, 8)])
+def test_bf16x3_folded_upconv_and_concat(shape):
+    from vtoonify_b200 import ops
+    from oracle import vt_oracle as O
+    B, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + 3)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) / np.sqrt(Cin * 9)
+    k4 = O.make_kernel([1, 3, 3, 1]) * 4
+    bias = torch.randn(Cout, generator=g); noise = torch.randn((B, 1, 2 * H, 2 * W), generator=g); nw = torch.tensor([0.2])
+    ref = O.upfirdn2d(F.conv_transpose2d(x, w.transpose(0, 1), stride=2), k4, pad=(1, 1))
+    ref = F.leaky_relu(ref + nw * noise + bias.view(1, -1, 1, 1), 0.2) * 1.4142135
+    ops.set_precision("bf16x3")
+    try:
+        xn = ops.to_nhwc(x.cuda())
+        wf = ops.fold_upconv_weights(ops.prep_weights(w.cuda(), cin_pad=Cin), k4.cuda())
+        y = ops.conv_up2_folded_nhwc(xn, wf, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135)
+        assert maxerr(ops.to_nchw(y).cpu(), ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())
+        # virtual concat of two sources
+        x2 = torch.randn((B, 32, H, W), generator=g)
+        w2 = torch.randn((Cout, Cin + 32, 3, 3), generator=g) / np.sqrt((Cin + 32) * 9)
+        ref2 = F.conv2d(torch.cat([x, x2], 1), w2, padding=1)
+        y2 = ops.conv2d_nhwc([xn, ops.to_nhwc(x2.cuda())], ops.prep_weights(w2.cuda(), cin_pad=Cin + 32), ops.conv_taps(3, 1), 1, H, W)
+        assert maxerr(ops.to_nchw(y2).cpu(), ref2) <= BF16X3_TOL * max(1.0, ref2.abs().max().item())
+    finally:
+        ops.set_precision(ops.DEFAULT_PRECISION)
+
+
+@pytest.mark.parametrize("transpose,pair_y", [(0, 0), (0, 1), (2, 0), (2, 1)])
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[4], CASES[5], (2, 32, 32, 33, 20, 3, 1, 1, 1), (1, 64, 64, 9, 40, 1, 1, 0, 1),
+                                  (1, 512, 512, 24, 16, 3, 1, 1, 1)])
+def test_tc_transposed_view_and_pair_orientation(case, transpose, pair_y):
+    """The planner may hand the problem to the kernel transposed (x <-> y) and stack CTA pairs along y; both are pure
+    re-indexings and must not change results (noise, residual and bias exercise every strided epilogue read)."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007 + 5)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn((B, Cout, H, W), generator=g)
+    noise = torch.randn((B, 1, H, W), generator=g); nw = torch.tensor([0.3])
+    kw = dict(act=_lib.ACT_LRELU, slope=0.2, gain=1.25, alpha=0.5, beta=0.75, noise=noise.cuda(), noise_w=nw.cuda())
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    lib = _lib.load()
+    old = (lib.vt_set_option(b"tc_transpose", transpose), lib.vt_set_option(b"tc_pair_y", pair_y))
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "bf16x3", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    finally:
+        lib.vt_set_option(b"tc_transpose", old[0]); lib.vt_set_option(b"tc_pair_y", old[1])
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    scale = max(1.0, ref.abs().max().item())
+    assert maxerr(y, ref) <= BF16X3_TOL * scale, f"T {transpose} pair_y {pair_y}: {maxerr(y, ref):.3e} (scale {scale:.1f})"
+
+
+@pytest.mark.parametrize("transpose", [0, 2])
+@pytest.mark.parametrize("shape", [(2, 64, 32, 7, 9), (1, 128, 64, 16, 24)])
+def test_folded_upconv_transposed_view(shape, transpose):
+    from vtoonify_b200 import _lib, ops
+    from oracle import vt_oracle as O
+    B, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + 9)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) / np.sqrt(Cin * 9)
+    k4 = O.make_kernel([1, 3, 3, 1]) * 4
+    bias = torch.randn(Cout, generator=g); noise = torch.randn((B, 1, 2 * H, 2 * W), generator=g); nw = torch.tensor([0.2])
+    ref = O.upfirdn2d(F.conv_transpose2d(x, w.transpose(0, 1), stride=2), k4, pad=(1, 1))
+    ref = F.leaky_relu(ref + nw * noise + bias.view(1, -1, 1, 1), 0.2) * 1.4142135
+    lib = _lib.load()
+    old = lib.vt_set_option(b"tc_transpose", transpose)
+    ops.set_precision("bf16x3")
+    try:
+        xn = ops.to_nhwc(x.cuda())
+        wf = ops.fold_upconv_weights(ops.prep_weights(w.cuda(), cin_pad=Cin), k4.cuda())
+        y = ops.conv_up2_folded_nhwc(xn, wf, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(), act=1, gain=1.4142135)
+        assert maxerr(ops.to_nchw(y).cpu(), ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())
+    finally:
+        lib.vt_set_option(b"tc_transpose", old)
+        ops.set_precision(ops.DEFAULT_PRECISION)

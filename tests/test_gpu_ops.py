@@ -180,7 +180,7 @@ def test_fir_nhwc_vs_oracle():
     k2 = torch.randn((3, 2), generator=g)
     y2 = ops.fir_nhwc(ops.to_nhwc(x.cuda()), k2.cuda(), (2, 1))
     assert maxerr(ops.to_nchw(y2).cpu(), O.upfirdn2d(x, k2, pad=(2, 1))) <= 1e-5
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 def test_adain_vs_oracle():
@@ -201,7 +201,7 @@ def test_adain_vs_oracle():
     y2 = ops.to_nchw(ops.adain_apply(ops.to_nhwc(x.cuda()), st2, gb2.cuda(), ops.to_nhwc(x2.cuda()))).cpu()
     ref2 = gb2[:, :128, None, None] * F.instance_norm(cat, eps=1e-5) + gb2[:, 128:, None, None]
     assert maxerr(y2, ref2) <= 2e-5
-    ops.set_precision("tf32")
+    ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 def test_upfirdn2d_tiled_and_generic_kernels_agree():

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("tf32", 3e-2)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("bf16x3", 2e-4), ("tf32", 3e-2)])
 def test_psp_encoder(golden, prec, tol):
     from vtoonify_b200 import ops
     from vtoonify_b200.psp import GradualStyleEncoder
@@ -26,7 +26,7 @@ def test_psp_encoder(golden, prec, tol):
     try:
         y = m(torch.from_numpy(g["x"]).float().cuda())
     finally:
-        ops.set_precision("tf32")
+        ops.set_precision(ops.DEFAULT_PRECISION)
     ref = torch.from_numpy(g["y"])
     assert tuple(y.shape) == (1, 18, 512)
     err = (y.cpu() - ref).abs().max().item()

@@ -8,7 +8,8 @@ import torch
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
-TOL = {"fp32": 2e-4, "tf32": 2e-2}     # max-abs error as a fraction of max(1, ref rms); measured values are printed
+TOL = {"fp32": 2e-4, "bf16x3": 1e-3, "tf32": 2e-2}     # max-abs error as a fraction of max(1, ref rms); measured values are printed.
+# bf16x3 is the product path: 1e-3 per pixel is the north_star bar (BASELINE.json); tf32 is the opt-in fast mode.
 
 
 def T(a):
@@ -29,7 +30,7 @@ def model(request):
     return request.param, m.cuda()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "tf32"])
 def test_forward_golden(golden, model, prec):
     from vtoonify_b200 import ops
     tag, m = model
@@ -42,7 +43,7 @@ def test_forward_golden(golden, model, prec):
                 y, masks = m(x, style, d_s=0.5, return_mask=True)
                 for i, mk in enumerate(masks):
                     e = (mk.cpu() - T(g[f"{case}_mask{i}"])).abs().max().item()
-                    assert e <= (1e-4 if prec == "fp32" else 3e-2), f"mask {i}: {e}"
+                    assert e <= {"fp32": 1e-4, "bf16x3": 5e-4, "tf32": 3e-2}[prec], f"mask {i}: {e}"
             else:
                 y = m(x, style, d_s=0.5)
             ref = T(g[f"{case}_y"])
@@ -52,7 +53,7 @@ def test_forward_golden(golden, model, prec):
             print(f"VToonify-{tag} case {case} [{prec}]: max|err| {err:.3e}, ref rms {rms:.3f}, err/rms {err / rms:.2e}")
             assert err <= TOL[prec] * max(1.0, rms)
     finally:
-        ops.set_precision("tf32")
+        ops.set_precision(ops.DEFAULT_PRECISION)
 
 
 def test_aux_paths(golden, model):

@@ -24,7 +24,8 @@ def report(name, fn, flops):
     def pct(i): return 100 * d[:, i].mean().item() / max(tot, 1)
     print(f"{name:30s} {ms:7.3f} ms {flops / ms / 1e9:5.0f} TF/s cyc/CTA {tot:9.0f} | prod A-empty {pct(1):4.1f} B-empty {pct(2):4.1f} "
           f"| mma A-full {pct(6):4.1f} B-full {pct(7):4.1f} tmem-empty {pct(8):4.1f} "
-          f"| epi tmem-full {pct(11):4.1f} tmem-ld {pct(12):4.1f} math {pct(13):4.1f} stage+store {pct(14):4.1f}")
+          f"| epi tmem-full {pct(11):4.1f} tmem-ld {pct(12):4.1f} math {pct(13):4.1f} stage+store {pct(14):4.1f}"
+          f" | xform tma-wait {pct(15):4.1f}")
 
 
 def conv_case(B, Cin, Cout, H, W, k=3, dil=1):
@@ -45,6 +46,8 @@ def up_case(B, Cin, Cout, H, W):
     report(f"up {Cin}->{Cout} {H}x{W} B{B}", fn, 2.0 * B * H * W * Cout * Cin * 36)
 
 
+ops.set_precision(sys.argv[1] if len(sys.argv) > 1 else ops.DEFAULT_PRECISION)
+print("precision", ops.get_precision())
 with torch.no_grad():
     conv_case(4, 512, 512, 72, 128)
     conv_case(4, 256, 256, 288, 512)
@@ -54,3 +57,4 @@ with torch.no_grad():
     up_case(4, 64, 32, 1152, 2048)
     up_case(4, 128, 64, 576, 1024)
     up_case(4, 512, 256, 144, 256)
+    conv_case(4, 256, 128, 576, 1024)

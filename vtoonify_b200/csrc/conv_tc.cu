@@ -21,6 +21,7 @@
 // plain convs (model/vtoonify.py:96-97,111-113,162-182) are the same GEMM here; a stride-2 transposed conv is 4 polyphase
 // calls, a stride-2 conv reads 4 parity views of the input (see make_views()).
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 #include <mutex>
 
 using namespace vt_tc;
@@ -65,6 +66,8 @@ struct TcArgs {
   // fused ToRGB tail
   const float* rgb_w; const float* rgb_bias; const float* rgb_skip; const float* rgb_skip_kernel; float* rgb_out;
   const float* slope_vec;
+  int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
+  int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
 };
 
 #define VT_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
@@ -90,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
   auto t_full = [&](int i) { return bar_base + 256u + 8u * i; };
   auto t_empty = [&](int i) { return bar_base + 272u + 8u * i; };
   const uint32_t tmem_slot = bar_base + 288u;
+  auto a_ready = [&](int i) { return bar_base + 320u + 8u * i; };   // bf16x3: A stage converted to [hi|lo] bf16 rows
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,7 +110,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     for (int ph = 0; ph < p.n_phase; ++ph) tma_prefetch_desc(&p.out_map[ph]);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); mbar_init(a_ready(i), 2 * CG); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4 * CG); }
     fence_barrier_init();
@@ -123,8 +127,11 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
 
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
-  const int item_w = TILE_W * p.mt * CG;        // output columns covered by one work item (of the CTA pair if CG == 2)
-  const int rank_x = (int)rank * TILE_W * p.mt; // this CTA's column offset inside the work item
+  // a work item covers item_w x item_h output pixels (of the CTA pair if CG == 2; the pair is side by side or stacked)
+  const int item_w = TILE_W * p.mt * ((CG == 2 && !p.pair_y) ? 2 : 1);
+  const int item_h = TILE_H * ((CG == 2 && p.pair_y) ? 2 : 1);
+  const int rank_x = p.pair_y ? 0 : (int)rank * TILE_W * p.mt;   // this CTA's offset inside the work item
+  const int rank_y = p.pair_y ? (int)rank * TILE_H : 0;
 
   if (warp == 0) {
     // ================= TMA producer (whole warp converged; one elected lane issues) =================
@@ -137,7 +144,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
-      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w + rank_x;
+      const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
       const int wb = p.wB > 1 ? b : 0;
       for (int s = 0; s < p.n_src; ++s) {
@@ -146,10 +153,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           if (p.halo) {
             VT_TWAIT(0, mbar_wait(a_empty(a_st), a_par ^ 1, 1));
             if (elect_one()) {
-              if (CG == 2) {
+              if (CG == 2 && !p.bf16x3) {
                 if (rank == 0) mbar_arrive_expect_tx(a_full(a_st), 2u * (uint32_t)p.a_tx_bytes);
                 tma_load_4d_2sm(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
-              } else {
+              } else {   // (bf16x3: every CTA's transform warps wait on their own a_full)
                 mbar_arrive_expect_tx(a_full(a_st), (uint32_t)p.a_tx_bytes);
                 tma_load_4d(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
               }
@@ -173,13 +180,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               // one TMA box carries the weight tiles of `tgroup` consecutive taps: (32 ch, block_n, tgroup, 1)
               VT_TWAIT(1, mbar_wait(b_empty(b_st), b_par ^ 1, 3));
               if (elect_one()) {
+                // bf16x3: the weight row of a 32-channel chunk is one 128-byte bf16 row [w_hi(32) | w_lo(32)]
+                const int wc = p.bf16x3 ? (p.coff[s] + c0) * 2 : p.coff[s] + c0;
                 if (CG == 2) {   // this CTA stages rows [rank*block_n/2, +block_n/2) of the weight tile
                   if (rank == 0) mbar_arrive_expect_tx(b_full(b_st), 2u * (uint32_t)p.b_tx_bytes);
-                  tma_load_4d_2sm(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), p.coff[s] + c0,
+                  tma_load_4d_2sm(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), wc,
                                   n0 + (int)rank * (p.block_n / 2), p.step_w[j], wb);
                 } else {
                   mbar_arrive_expect_tx(b_full(b_st), (uint32_t)p.b_tx_bytes);
-                  tma_load_4d(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), p.coff[s] + c0, n0, p.step_w[j], wb);
+                  tma_load_4d(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), wc, n0, p.step_w[j], wb);
                 }
               }
               __syncwarp();
@@ -192,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     }
   } else if (warp == 1 && rank == 0) {
     // ================= MMA issuer (whole warp converged; one elected lane issues; CTA rank 0 only) =================
-    const uint32_t idesc = make_idesc_tf32(TILE_M * CG, p.block_n);
+    const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(TILE_M * CG, p.block_n) : make_idesc_tf32(TILE_M * CG, p.block_n);
     int a_st = 0, b_st = 0, as = 0;
     uint32_t a_par = 0, b_par = 0, t_par = 0;
     const uint32_t tile_bytes_n = (uint32_t)(p.block_n / CG) * 128u;   // bytes of one tap's weight rows held by this CTA
@@ -204,12 +213,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       for (int s = 0; s < p.n_src; ++s) {
         for (int kc = 0; kc < p.kchunks[s]; ++kc) {
           if (p.halo) {
-            VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 5));
+            VT_TWAIT(0, mbar_wait(p.bf16x3 ? a_ready(a_st) : a_full(a_st), a_par, 5));
           }
           int gj = 0;
           for (int j = 0; j < p.n_steps; ++j) {
             if (!p.halo) {
-              VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 6));
+              VT_TWAIT(0, mbar_wait(p.bf16x3 ? a_ready(a_st) : a_full(a_st), a_par, 6));
             }
             if (gj == 0) {
               VT_TWAIT(1, mbar_wait(b_full(b_st), b_par, 7));
@@ -230,7 +239,25 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               for (int g = 0; g < p.mt; ++g) {
                 const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)(g * TILE_W * 128), sbo, 0);
                 const uint32_t d_tmem = d_tmem0 + (uint32_t)(g * p.block_n);
-                if (CG == 2) {
+                if (p.bf16x3) {
+                  // a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the dropped a_lo*w_lo term is ~2^-18 relative). The A row is
+                  // [a_hi(32)|a_lo(32)] and the B row [w_hi(32)|w_lo(32)] bf16; +2 on a descriptor = +32 B = 16 bf16 of K.
+                  if (CG == 2) {
+                    umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                    umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                    umma_bf16_2sm(d_tmem, adesc + 4, bdesc, idesc, 1);
+                    umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 2, idesc, 1);
+                    umma_bf16_2sm(d_tmem, adesc, bdesc + 4, idesc, 1);
+                    umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 6, idesc, 1);
+                  } else {
+                    umma_bf16(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                    umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                    umma_bf16(d_tmem, adesc + 4, bdesc, idesc, 1);
+                    umma_bf16(d_tmem, adesc + 6, bdesc + 2, idesc, 1);
+                    umma_bf16(d_tmem, adesc, bdesc + 4, idesc, 1);
+                    umma_bf16(d_tmem, adesc + 2, bdesc + 6, idesc, 1);
+                  }
+                } else if (CG == 2) {
                   umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, first ^ 1u);
                   umma_tf32_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                   umma_tf32_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
@@ -261,6 +288,54 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       __syncwarp();
       if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
+  } else if ((warp == 2 || warp == 3) && p.bf16x3) {
+    // ================= operand transform (bf16x3): fp32 rows -> [hi(32) | lo(32)] bf16 rows, in place =================
+    // A 32-channel fp32 row (128 B) becomes the K = 64 bf16 row [a_hi | a_lo] with a_hi = bf16(a), a_lo = bf16(a - a_hi);
+    // 16-byte chunk j of the row lives at physical chunk j ^ ((addr >> 7) & 7) (SWIZZLE_128B as TMA wrote it, kept for the MMA).
+    const int t = (warp - 2) * 32 + lane;
+    const int rows = p.a_tx_bytes >> 7;
+    int a_st = 0;
+    uint32_t a_par = 0;
+    for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
+      for (int s = 0; s < p.n_src; ++s) {
+        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+          const int loads = p.halo ? 1 : p.n_steps;
+          for (int l = 0; l < loads; ++l) {
+            VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 9));
+            const uint32_t stage = a_base + a_st * p.a_stage_bytes;
+            for (int r = t; r < rows; r += 64) {
+              const uint32_t row = stage + (uint32_t)r * 128u;
+              const uint32_t ph = (row >> 7) & 7u;
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(row + ((j ^ ph) << 4)));
+                f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+              }
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
+                hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((m ^ ph) << 4)), "r"(hi[4 * m]), "r"(hi[4 * m + 1]), "r"(hi[4 * m + 2]), "r"(hi[4 * m + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((m + 4) ^ ph) << 4)), "r"(lo[4 * m]), "r"(lo[4 * m + 1]), "r"(lo[4 * m + 2]), "r"(lo[4 * m + 3]) : "memory");
+              }
+            }
+            fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cta0_release(a_ready(a_st)); else mbar_arrive(a_ready(a_st)); }
+            if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int q = warp - 4;
@@ -275,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
       const int n_tile = tile / m_tiles, m = tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
-      const int oy0 = (rem / p.tiles_x) * TILE_H, ox0 = (rem % p.tiles_x) * item_w + rank_x;
+      const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
       VT_TWAIT(0, mbar_wait(t_full(as), t_par, 8));
       tc_fence_after();
@@ -443,6 +518,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     o[0] = (unsigned long long)(clock64() - t_begin);
     o[1] = (unsigned long long)tw[0]; o[2] = (unsigned long long)tw[1]; o[3] = (unsigned long long)tw[2]; o[4] = (unsigned long long)tw[3];
   }
+  if (p.dbg && lane == 0 && warp == 2 && p.bf16x3) p.dbg[(size_t)blockIdx.x * 16 + 15] = (unsigned long long)tw[0];   // transform: wait for TMA
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
@@ -472,7 +548,7 @@ PFN_encodeTiled get_encode() {
 
 // 4-D fp32 tensor map, SWIZZLE_128B, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..3.
 int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3], const uint32_t box[4],
-              const char* what) {
+              const char* what, bool bf16 = false) {
   PFN_encodeTiled enc = get_encode();
   VT_CHECK(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -482,7 +558,7 @@ int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   for (int i = 0; i < 4; ++i) VT_CHECK(gd[i] >= 1 && bx[i] >= 1 && bx[i] <= 256, "conv_tc: bad %s map dim %d (dim=%llu box=%u)", what, i, (unsigned long long)gd[i], bx[i]);
   for (int i = 0; i < 3; ++i) VT_CHECK(gs[i] % 16 == 0 && gs[i] > 0, "conv_tc: %s map stride %d (%llu B) not a positive multiple of 16", what, i, (unsigned long long)gs[i]);
   VT_CHECK(((uintptr_t)base & 15) == 0, "conv_tc: %s base pointer not 16-byte aligned", what);
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VT_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
@@ -493,6 +569,8 @@ int g_tc_mode = 1;  // 0: one TMA box per tap; 1: one halo box per K chunk + row
 int g_tc_mt = 0;    // 0: automatic M-tiles per work item; 1/2/4: forced
 unsigned long long* g_tc_dbg = nullptr;   // device buffer [148][16] set through vt_set_debug_buffer (tuning only)
 int g_tc_cg2 = 1;     // 1: use CTA pairs (cta_group::2, M = 256) for N-tile-256 stride-1 halo convolutions
+int g_tc_transpose = 1;   // 1: hand the problem over transposed when that wastes fewer tiles; 0: never; 2: always (tests)
+int g_tc_pair_y = -1;     // -1: automatic pair orientation; 0/1: forced (tests)
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
@@ -508,6 +586,7 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(d->out_sx % 4 == 0 && d->out_sy % 4 == 0 && d->out_sb % 4 == 0, "conv_tc: output strides must be multiples of 4 floats");
   VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
+  VT_SUP(!d->weight_bf16x3 || d->w_cstride % KCH == 0, "conv_tc: bf16x3 weights need a channel stride that is a multiple of 32");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
   VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
   VT_SUP(!d->slope_vec || (((uintptr_t)d->slope_vec & 15) == 0), "conv_tc: slope_vec not 16-byte aligned");
@@ -525,6 +604,8 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
+  if (key && strcmp(key, "tc_transpose") == 0) { int old = g_tc_transpose; g_tc_transpose = value; return old; }
+  if (key && strcmp(key, "tc_pair_y") == 0) { int old = g_tc_pair_y; g_tc_pair_y = value; return old; }
   if (key && strcmp(key, "upfirdn_tiled") == 0) { int old = g_upfirdn_tiled; g_upfirdn_tiled = value; return old; }
   return -1;
 }
@@ -542,15 +623,27 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
 
   static thread_local TcArgs a;  // large (tensor maps); reused to avoid stack churn
   memset(&a, 0, sizeof(a));
+
+  // ---- geometry view. The kernel's M tile is 8 pixels along "x" by 16 along "y". When that wastes fewer tiles the
+  // problem is handed over transposed (x <-> y): only strides, extents and tap offsets swap roles, the data stays put.
+  // (72x128 maps: 16x5 = 80 tiles as is, 9x8 = 72 transposed.)
+  bool T = false;
+  if (g_tc_transpose && d->stride == 1 && !d->rgb_w) {
+    const int64_t t0 = vt_cdiv(d->Wo, TILE_W) * vt_cdiv(d->Ho, TILE_H), t1 = vt_cdiv(d->Ho, TILE_W) * vt_cdiv(d->Wo, TILE_H);
+    T = (g_tc_transpose == 2) || (t1 < t0);
+  }
+  const int gH = T ? d->W : d->H, gW = T ? d->H : d->W, gHo = T ? d->Wo : d->Ho, gWo = T ? d->Ho : d->Wo;
+  const int64_t g_out_sy = T ? d->out_sx : d->out_sy, g_out_sx = T ? d->out_sy : d->out_sx;
+
   a.n_phase = d->n_phase;
-  a.Ho = d->Ho; a.Wo = d->Wo; a.Cout = d->Cout; a.wB = d->wB; a.out_cpitch = d->out_cpitch;
+  a.Ho = gHo; a.Wo = gWo; a.Cout = d->Cout; a.wB = d->wB; a.out_cpitch = d->out_cpitch;
   a.bias = d->bias; a.noise = d->noise; a.noise_w = d->noise_w; a.res = d->res;
-  a.out_sb = d->out_sb; a.out_sy = d->out_sy; a.out_sx = d->out_sx;
+  a.out_sb = d->out_sb; a.out_sy = g_out_sy; a.out_sx = g_out_sx;
   for (int ph = 0; ph < 4; ++ph) a.phase_off[ph] = d->phase_off[ph < d->n_phase ? ph : 0];
   if (d->noise) {
     VT_CHECK(d->out_sb % d->out_cpitch == 0 && d->out_sy % d->out_cpitch == 0 && d->out_sx % d->out_cpitch == 0,
              "conv_tc: output strides must be multiples of out_cpitch when noise is used");
-    a.pix_sb = d->out_sb / d->out_cpitch; a.pix_sy = d->out_sy / d->out_cpitch; a.pix_sx = d->out_sx / d->out_cpitch;
+    a.pix_sb = d->out_sb / d->out_cpitch; a.pix_sy = g_out_sy / d->out_cpitch; a.pix_sx = g_out_sx / d->out_cpitch;
     for (int ph = 0; ph < 4; ++ph) {
       VT_CHECK(a.phase_off[ph] % d->out_cpitch == 0, "conv_tc: phase offset must be a multiple of out_cpitch");
       a.phase_pix[ph] = a.phase_off[ph] / d->out_cpitch;
@@ -561,6 +654,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.rgb_w = d->rgb_w; a.rgb_bias = d->rgb_bias; a.rgb_skip = d->rgb_skip; a.rgb_skip_kernel = d->rgb_skip_kernel; a.rgb_out = d->rgb_out;
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;
+  a.bf16x3 = d->weight_bf16x3 != nullptr;
 
   // ---- K iteration space
   a.n_src = d->n_src;
@@ -569,12 +663,13 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.n_steps = d->taps;
   int dxmin = 1 << 30, dxmax = -(1 << 30), dymin = 1 << 30, dymax = -(1 << 30);
   for (int t = 0; t < d->taps; ++t) {
-    int view = 0, vx = d->tap_dx[t], vy = d->tap_dy[t];
+    const int tdx = T ? d->tap_dy[t] : d->tap_dx[t], tdy = T ? d->tap_dx[t] : d->tap_dy[t];
+    int view = 0, vx = tdx, vy = tdy;
     if (d->stride == 2) {
-      const int px = d->tap_dx[t] & 1, py = d->tap_dy[t] & 1;
+      const int px = tdx & 1, py = tdy & 1;
       view = py * 2 + px;
-      vx = (d->tap_dx[t] - px) / 2;
-      vy = (d->tap_dy[t] - py) / 2;
+      vx = (tdx - px) / 2;
+      vy = (tdy - py) / 2;
     }
     VT_CHECK(vx >= -100 && vx <= 100 && vy >= -100 && vy <= 100, "conv_tc: tap offset out of range");
     a.step_view[t] = (int8_t)view; a.step_vx[t] = (int8_t)vx; a.step_vy[t] = (int8_t)vy;
@@ -597,7 +692,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     int want = (g_tc_mt > 0) ? g_tc_mt : (bn >= 256 ? 1 : (bn >= 128 ? 2 : 4));
     // keep two accumulator stages (epilogue/mainloop overlap) unless forced: 2 * n_phase * mt * bn <= 512 TMEM columns
     const int col_budget = (g_tc_mt > 0) ? 512 : ((2 * bn <= 512) ? 256 : 512);
-    while (want > 1 && (want * bn > col_budget || d->Wo <= TILE_W * (want / 2))) want /= 2;
+    while (want > 1 && (want * bn > col_budget || gWo <= TILE_W * (want / 2))) want /= 2;
     mt = want;
   }
   const int fixed = 2 * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
@@ -613,22 +708,23 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
       if (ok) { tgroup = tg; break; }
     }
   }
-  // CTA pairs: N tile 256, stride-1 halo mode, one M tile per CTA, one tap per weight box
+  // CTA pairs (cta_group::2, one MMA instruction covers M = 256 pixels): stride-1 halo mode. g_tc_cg2: 1 = every eligible
+  // layer (small-N layers are bound by MMA issue, a pair halves the instructions per pixel), 2 = only N tile 256.
   const int halo1_bytes = (TILE_W + (dxmax - dxmin)) * (TILE_H + (dymax - dymin)) * 128;
-  const int cg = (g_tc_cg2 && can_halo && bn == 256 && mt == 1 && tgroup == 1 && d->Wo > TILE_W &&
-                  halo1_bytes <= d->taps * TILE_M * 128 / 2 && halo1_bytes <= 96 * 1024) ? 2 : 1;
+  int cg = (g_tc_cg2 && can_halo && (bn == 256 || g_tc_cg2 == 1) && (gWo > TILE_W * mt || gHo > TILE_H) &&
+            halo1_bytes <= d->taps * TILE_M * 128 / 2 && halo1_bytes <= 96 * 1024) ? 2 : 1;
   a.tgroup = tgroup;
   for (int t = 0; t < d->taps && t < 32; ++t) {
     if (t % tgroup == 0) a.grp_first_mask |= 1 << t;
     if (t % tgroup == tgroup - 1) a.grp_last_mask |= 1 << t;
   }
-  a.b_tx_bytes = (bn / cg) * 128 * tgroup;
   for (;; mt /= 2) {
     const int halo_w = TILE_W * mt + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
     const int halo_bytes = halo_w * halo_h * 128;
     a.halo = can_halo && halo_w <= 256 && halo_h <= 256 && halo_bytes <= 96 * 1024 &&
              (mt > 1 || halo_bytes <= d->taps * TILE_M * 128 / 2);
     if (!a.halo && mt > 1) continue;
+    if (!a.halo) cg = 1;
     a.halo_x0 = dxmin; a.halo_y0 = dymin; a.halo_w = halo_w;
     a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
     // shared memory plan: A ring (halo boxes or per-tap tiles) + B ring (weight tiles) + 2 output staging buffers
@@ -645,6 +741,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed;
     if (smem_bytes <= MAX_SMEM || mt == 1) break;
   }
+  a.b_tx_bytes = (bn / cg) * 128 * tgroup;
   VT_CHECK(smem_bytes <= MAX_SMEM && a.a_stages >= 2 && a.b_stages >= 2 && a.a_stages <= 8 && a.b_stages <= 8,
            "conv_tc: shared memory plan does not fit (%d B, mt=%d, bn=%d)", smem_bytes, mt, bn);
   for (int t = 0; t < d->taps; ++t)
@@ -656,18 +753,24 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.tmem_cols = tc;
   a.block_n = bn;
   a.n_tiles = n_eff / bn;
-  a.tiles_x = (int)vt_cdiv(d->Wo, TILE_W * mt * cg);
-  a.tiles_y = (int)vt_cdiv(d->Ho, TILE_H);
+  // pair orientation: side by side (x) or stacked (y), whichever wastes fewer tiles; ties -> x
+  if (cg == 2) {
+    const int64_t px = vt_cdiv(gWo, TILE_W * mt * 2) * vt_cdiv(gHo, TILE_H), py = vt_cdiv(gWo, TILE_W * mt) * vt_cdiv(gHo, TILE_H * 2);
+    a.pair_y = (g_tc_pair_y >= 0) ? g_tc_pair_y : (py < px ? 1 : 0);
+  }
+  a.tiles_x = (int)vt_cdiv(gWo, TILE_W * mt * ((cg == 2 && !a.pair_y) ? 2 : 1));
+  a.tiles_y = (int)vt_cdiv(gHo, TILE_H * ((cg == 2 && a.pair_y) ? 2 : 1));
   const int64_t total = (int64_t)a.n_tiles * a.B * a.tiles_x * a.tiles_y;
   VT_CHECK(total < (1LL << 31), "conv_tc: too many tiles");
   a.total_tiles = (int)total;
 
-  // ---- tensor maps
+  // ---- tensor maps (dims innermost first: channels, kernel-x, kernel-y, batch)
   for (int s = 0; s < d->n_src; ++s) {
     const uint64_t cs = (uint64_t)d->src_cstride[s];
     if (d->stride == 1) {
-      const uint64_t dims[4] = {cs, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
-      const uint64_t str[3] = {cs * 4, (uint64_t)d->W * cs * 4, (uint64_t)d->H * d->W * cs * 4};
+      const uint64_t real_sx = cs * 4, real_sy = (uint64_t)d->W * cs * 4;
+      const uint64_t dims[4] = {cs, (uint64_t)gW, (uint64_t)gH, (uint64_t)d->B};
+      const uint64_t str[3] = {T ? real_sy : real_sx, T ? real_sx : real_sy, (uint64_t)d->H * d->W * cs * 4};
       const uint32_t box[4] = {KCH, (uint32_t)(a.halo ? a.halo_w : TILE_W),
                                (uint32_t)(a.halo ? TILE_H + (dymax - dymin) : TILE_H), 1};
       if (make_map4(&a.in_map[s][0], d->src[s], dims, str, box, "input")) return 1;
@@ -692,12 +795,19 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     const uint64_t wc = (uint64_t)d->w_cstride;
     const uint64_t dims[4] = {wc, (uint64_t)n_eff, (uint64_t)d->w_taps, (uint64_t)d->wB};
     const uint64_t str[3] = {wc * 4, (uint64_t)n_eff * wc * 4, (uint64_t)d->w_taps * n_eff * wc * 4};
-    const uint32_t box[4] = {KCH, (uint32_t)(bn / cg), (uint32_t)a.tgroup, 1};
-    if (make_map4(&a.w_map, d->weight, dims, str, box, "weight")) return 1;
+    if (a.bf16x3) {   // same byte layout as the fp32 tensor: every 32-channel chunk is [w_hi(32) | w_lo(32)] bf16
+      VT_CHECK(((uintptr_t)d->weight_bf16x3 & 15) == 0, "conv_tc: weight_bf16x3 not 16-byte aligned");
+      const uint64_t dims2[4] = {2 * wc, (uint64_t)n_eff, (uint64_t)d->w_taps, (uint64_t)d->wB};
+      const uint32_t box[4] = {2 * KCH, (uint32_t)(bn / cg), (uint32_t)a.tgroup, 1};
+      if (make_map4(&a.w_map, d->weight_bf16x3, dims2, str, box, "weight(bf16x3)", true)) return 1;
+    } else {
+      const uint32_t box[4] = {KCH, (uint32_t)(bn / cg), (uint32_t)a.tgroup, 1};
+      if (make_map4(&a.w_map, d->weight, dims, str, box, "weight")) return 1;
+    }
   }
   for (int ph = 0; ph < d->n_phase; ++ph) {
-    const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
-    const uint64_t str[3] = {(uint64_t)d->out_sx * 4, (uint64_t)d->out_sy * 4, (uint64_t)d->out_sb * 4};
+    const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)gWo, (uint64_t)gHo, (uint64_t)d->B};
+    const uint64_t str[3] = {(uint64_t)g_out_sx * 4, (uint64_t)g_out_sy * 4, (uint64_t)d->out_sb * 4};
     const uint32_t box[4] = {32, TILE_W, TILE_H, 1};
     if (make_map4(&a.out_map[ph], d->out + d->phase_off[ph], dims, str, box, "output")) return 1;
   }

@@ -8,6 +8,7 @@
 //                             128-byte multiples so a TMA box of 32 channels is one swizzle row).
 //                             With style == NULL it is the plain re-layout used for nn.Conv2d / EqualConv2d weights.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -183,6 +184,37 @@ extern "C" int vt_modulate_weights_f32(const float* W, const float* style, float
   dim3 grid((unsigned)Cout, (unsigned)wB);
   modulate_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, style, out, Cout, Cin, kh * kw, cin_pad, scale,
                                                                  demodulate, round_tf32);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- bf16x3 weight split -----------------------------------------------------------------------------------------
+// one thread per (row, 32-channel chunk, 4-channel group): reads a float4, writes 2 bf16x4 halves
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ w, uint2* __restrict__ out, int64_t n_quads) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  unsigned short h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(f[k]);
+    h[k] = __bfloat16_as_ushort(hb);
+    l[k] = __bfloat16_as_ushort(__float2bfloat16_rn(f[k] - __bfloat162float(hb)));
+  }
+  const int64_t chunk = i >> 3;          // 8 quads per 32-channel chunk
+  const int q = (int)(i & 7);
+  uint2* base = out + chunk * 16;        // a chunk is 128 bytes = 16 uint2
+  base[q] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  base[8 + q] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+extern "C" int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, void* stream) {
+  VT_CHECK(w && out && rows >= 1 && C >= 32 && C % 32 == 0, "split_weights_bf16x3: bad args (rows=%lld C=%d)", (long long)rows, C);
+  VT_CHECK(((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 15) == 0, "split_weights_bf16x3: pointers must be 16-byte aligned");
+  const int64_t n_quads = rows * C / 4;
+  split_bf16x3_kernel<<<(unsigned)vt_cdiv(n_quads, 256), 256, 0, (cudaStream_t)stream>>>(w, (uint2*)out, n_quads);
   VT_LAUNCH_CHECK();
   return 0;
 }

@@ -14,15 +14,21 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU_TANH, ConvDesc, SmallNDesc, chec
 
 SQRT2 = math.sqrt(2.0)
 
-# "tf32": tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate) — the product path.
+# "bf16x3" (default, the product path): tcgen05 tensor-core convolutions that meet the 1e-3 per-pixel parity bar — the kernel
+#   below with
+# "tf32": tcgen05 tensor-core convolutions with TF32 operands (fp32 accumulate): ~20% faster end to end, but 10-bit mantissas
+#   put the 50-layer VToonify-D output 2.8-4e-3 away from the fp32 reference (measured), above the parity bar. Opt-in.
+# "bf16x3": the same tensor-core kernel with every fp32 operand split into bf16 hi + lo parts in shared memory and three
+#   MMA products per K step (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate): fp32-class accuracy at 1.5x the MMA work.
 # "fp32": every convolution on the fp32-exact FFMA kernel (used to cross-check the tensor-core path).
-_precision = "tf32"
+DEFAULT_PRECISION = "bf16x3"
+_precision = DEFAULT_PRECISION
 
 
 def set_precision(p: str) -> str:
     global _precision
-    if p not in ("tf32", "fp32"):
-        raise ValueError("precision must be 'tf32' or 'fp32'")
+    if p not in ("tf32", "bf16x3", "fp32"):
+        raise ValueError("precision must be 'tf32', 'bf16x3' or 'fp32'")
     old, _precision = _precision, p
     return old
 
@@ -289,7 +295,10 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
         if rgb.get("skip") is not None:
             d.rgb_skip, d.rgb_skip_kernel = rgb["skip"].contiguous().data_ptr(), rgb["kernel"].contiguous().data_ptr()
     lib = _lib.load()
-    if prec == "tf32" and lib.vt_conv2d_tc_supported(d):
+    use_tc = prec in ("tf32", "bf16x3") and lib.vt_conv2d_tc_supported(d)
+    if use_tc and prec == "bf16x3":
+        d.weight_bf16x3 = split_weights_bf16x3(weight).data_ptr()
+    if use_tc:
         if _tc_profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             cin = sum(int(d.src_c[i]) for i in range(d.n_src))
@@ -306,9 +315,26 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     return out if rgb is None else (out, rgb_out)
 
 
+def split_weights_bf16x3(weight: torch.Tensor) -> torch.Tensor:
+    """``weight`` (from :func:`prep_weights` / :func:`fold_upconv_weights`, unrounded fp32, channel stride % 32 == 0) ->
+    same-shape buffer whose 32-channel chunks hold ``[bf16(w) | bf16(w - bf16(w))]``. Cached on the tensor object, so cached
+    plain-conv weights are split once; per-frame modulated weights are split per call (one tiny launch)."""
+    ver = weight._version
+    cached = getattr(weight, "_vt_bf16x3", None)
+    if cached is not None and cached[0] == ver and cached[1] == weight.data_ptr():
+        return cached[2]
+    if weight.shape[-1] % 32 != 0 or not weight.is_contiguous():
+        raise _lib.VtError("split_weights_bf16x3: weight channel stride must be a multiple of 32")
+    out = torch.empty_like(weight)
+    check(_lib.load().vt_split_weights_bf16x3(weight.data_ptr(), out.data_ptr(), weight.numel() // weight.shape[-1],
+                                             weight.shape[-1], _stream()))
+    weight._vt_bf16x3 = (ver, weight.data_ptr(), out)
+    return out
+
+
 def rgb_fusable(Cout: int, precision: Optional[str] = None) -> bool:
     """The ToRGB tail can ride in the conv epilogue when one N tile holds all channels (tensor-core path only)."""
-    return (precision or _precision) == "tf32" and Cout % 32 == 0 and Cout <= 256 and _options["fuse_torgb"]
+    return (precision or _precision) in ("tf32", "bf16x3") and Cout % 32 == 0 and Cout <= 256 and _options["fuse_torgb"]
 
 
 def conv_out_size(n: int, k: int, stride: int, padding: int, dilation: int) -> int:

@@ -235,6 +235,10 @@ def run_ours(args, rank, world, local_rank):
     for a, b, f, nb, label in prof:
         d = per.setdefault(label, [0.0, 0.0, 0])
         d[0] += a.elapsed_time(b); d[1] += f; d[2] += 1
+    if args.dump_layers:
+        with open(args.dump_layers, "w") as f:
+            for k, v in sorted(per.items(), key=lambda kv: -kv[1][0]):
+                f.write(f"{v[0] / args.steps:8.3f} ms  x{v[2] / args.steps:5.1f}  {v[1] / (v[0] * 1e-3) / 1e12:6.1f} TF/s  {k}\n")
     top = sorted(per.items(), key=lambda kv: -kv[1][0])[:6]
     # algorithmic-flop peak of the mode: TF32 = bf16 / 2; bf16x3 issues 3 bf16 products per algorithmic product = bf16 / 3
     div = 3.0 if args.precision == "bf16x3" else 2.0
@@ -290,6 +294,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--backbone", default="dualstylegan", choices=["dualstylegan", "toonify"])
+    ap.add_argument("--dump-layers", default=None, help="write the per-layer conv_tc timing table to this file")
     ap.add_argument("--precision", default="bf16x3", choices=["tf32", "bf16x3", "fp32"],
                     help="bf16x3 (default): split-operand tensor-core mode that meets the 1e-3 parity bar; tf32: faster, 3e-3 error")
     ap.add_argument("--height", type=int, default=H_IN)

@@ -145,6 +145,9 @@ typedef struct vt_conv_desc {
   const void*  weight_bf16x3;   /* optional: `weight` split by vt_split_weights_bf16x3 (same shape/strides in bytes). When set, the
                                  * tensor-core kernel computes a*w as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with bf16 operands
                                  * (fp32-class accuracy, 1.5x the MMA work of TF32); ignored by the direct kernel          */
+  const float* src_scale[2];    /* optional planar [B,H,W] per-pixel multiplier of source i, applied while the operand is split
+                                 * (bf16x3 tensor-core mode, stride 1 only): conv(cat[f_G, f_E * m_E]) without materialising
+                                 * f_E * m_E (model/vtoonify.py:127). Rejected by the other kernels.                        */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */
@@ -153,7 +156,7 @@ int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream);
  * Cout % 16 == 0, 16B-aligned views. */
 int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream);
 int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 accepts the descriptor */
-/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","upfirdn_tiled"};
+/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","smalln_is","upfirdn_tiled"};
  * returns the previous value (-1 for an unknown key) */
 int vt_set_option(const char* key, int value);
 /* tuning only: device buffer of 148*16 uint64 that conv_tc fills with per-role wait-cycle counters (NULL disables) */
@@ -183,6 +186,7 @@ typedef struct vt_smalln_desc {
   const float* mul_src;
   int32_t mul_c, round_tf32;
   const float* tap_const;       /* optional [wB][w_taps][Cout]: constant added per in-bounds tap (folded affine) */
+  const float* src_mask;        /* optional planar [B,H,W]: the NHWC source is multiplied per pixel by it (f_E * m_E)        */
 } vt_smalln_desc;
 int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream);
 /* Fold a per-(b,c) affine (AdaIN: gamma*(x-mean)*rstd+beta, model/dualstylegan.py:16-21) into conv weights:

@@ -383,3 +383,90 @@ def test_folded_upconv_transposed_view(shape, transpose):
     finally:
         lib.vt_set_option(b"tc_transpose", old)
         ops.set_precision(ops.DEFAULT_PRECISION)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 10, 12), (1, 128, 37, 70), (2, 32, 16, 32), (1, 256, 19, 33)])
+@pytest.mark.parametrize("n_out", [1, 2, 3, 4])
+def test_smalln_input_stationary_vs_gather_kernel(shape, n_out):
+    """The input-stationary 3x3 kernel (each pixel read once, 9 partial dots in smem, shifted sum) against the gather kernel
+    and torch: virtual concat [x | |x - x2|], per-tap constants, planar source, bias."""
+    from vtoonify_b200 import _lib, ops
+    ops.set_precision("fp32")
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + n_out)
+    x = torch.randn((B, C, H, W), generator=g); x2 = torch.randn((B, C, H, W), generator=g)
+    pl = torch.randn((B, 3, H, W), generator=g)
+    w = torch.randn((n_out, 2 * C, 3, 3), generator=g) / np.sqrt(18 * C); b = torch.randn(n_out, generator=g)
+    wpl_t = torch.randn((n_out, 3, 3, 3), generator=g) / 5
+    kc = torch.randn((1, 9, n_out), generator=g)          # per-tap constants (in-bounds taps only)
+    ones = F.conv2d(torch.ones((1, 1, H, W)), torch.eye(9).view(9, 1, 3, 3), padding=1)      # [1,9,H,W] tap-in-bounds mask
+    # conv taps are cross-correlation order (ky,kx) -> tap index ky*3+kx
+    const = torch.einsum("othw,tn->onhw", ones, kc[0])
+    ref = F.conv2d(torch.cat([x, (x - x2).abs()], 1), w, b, padding=1) + F.conv2d(pl, wpl_t, padding=1) + const
+    xn, x2n = ops.to_nhwc(x.cuda()), ops.to_nhwc(x2.cuda())
+    wp = ops.prep_weights(w.cuda(), cin_pad=2 * C)
+    wpl = wpl_t.permute(2, 3, 0, 1).reshape(9, n_out, 3).contiguous().cuda()
+    lib = _lib.load()
+    outs = []
+    for mode in (0, 2):
+        old = lib.vt_set_option(b"smalln_is", mode)
+        try:
+            y = ops.smalln_conv(xn, wp, ops.conv_taps(3, 1), n_out, B, H, W, planar=pl.cuda(), planar_weight=wpl, bias=b.cuda(),
+                                src2=x2n, tap_const=kc.cuda())
+        finally:
+            lib.vt_set_option(b"smalln_is", old)
+        outs.append(y.cpu())
+    ops.set_precision(ops.DEFAULT_PRECISION)
+    scale = max(1.0, ref.abs().max().item())
+    assert maxerr(outs[0], ref) <= 2e-5 * scale, f"gather kernel: {maxerr(outs[0], ref):.3e}"
+    assert maxerr(outs[1], ref) <= 2e-5 * scale, f"input-stationary kernel: {maxerr(outs[1], ref):.3e}"
+
+
+@pytest.mark.parametrize("transpose", [0, 2])
+@pytest.mark.parametrize("case", [(2, 32, 64, 19, 13, 3, 1), (1, 128, 128, 24, 40, 3, 1), (2, 64, 32, 9, 16, 1, 0)])
+def test_bf16x3_second_source_scaled_per_pixel(case, transpose):
+    """conv(cat[a, c * m]) with the planar map m applied while the c tiles are split (Fusion: f_E * m_E never materialised)."""
+    from vtoonify_b200 import _lib, ops
+    B, C1, Cout, H, W, k, pad = case
+    g = torch.Generator().manual_seed(sum(case) + 17)
+    a = torch.randn((B, C1, H, W), generator=g); c = torch.randn((B, 32, H, W), generator=g)
+    m = torch.rand((B, 1, H, W), generator=g)
+    w = torch.randn((Cout, C1 + 32, k, k), generator=g) / np.sqrt((C1 + 32) * k * k)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(torch.cat([a, c * m], 1), w, b, padding=pad)
+    lib = _lib.load()
+    old = lib.vt_set_option(b"tc_transpose", transpose)
+    ops.set_precision("bf16x3")
+    try:
+        y = ops.conv2d_nhwc([ops.to_nhwc(a.cuda()), ops.to_nhwc(c.cuda())], ops.prep_weights(w.cuda(), cin_pad=C1 + 32),
+                            ops.conv_taps(k, pad), 1, H, W, bias=b.cuda(), src_scale=[None, m.cuda()])
+        assert maxerr(ops.to_nchw(y).cpu(), ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())
+        with pytest.raises(_lib.VtError):   # the fp32 FFMA kernel does not implement it: must fail loudly, not ignore the map
+            ops.conv2d_nhwc([ops.to_nhwc(a.cuda()), ops.to_nhwc(c.cuda())], ops.prep_weights(w.cuda(), cin_pad=C1 + 32),
+                            ops.conv_taps(k, pad), 1, H, W, bias=b.cuda(), src_scale=[None, m.cuda()], precision="fp32")
+    finally:
+        lib.vt_set_option(b"tc_transpose", old)
+        ops.set_precision(ops.DEFAULT_PRECISION)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_smalln_masked_source(mode):
+    from vtoonify_b200 import _lib, ops
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(23)
+    B, C, H, W = 2, 64, 21, 37
+    x = torch.randn((B, C, H, W), generator=g); m = torch.rand((B, 1, H, W), generator=g)
+    pl = torch.randn((B, 3, H, W), generator=g)
+    w = torch.randn((3, C + 3, 3, 3), generator=g) / 24; b = torch.randn(3, generator=g)
+    ref = F.conv2d(torch.cat([pl, x * m], 1), w, b, padding=1)
+    wp = ops.prep_weights(w[:, 3:].contiguous().cuda(), cin_pad=C)
+    wpl = w[:, :3].permute(2, 3, 0, 1).reshape(9, 3, 3).contiguous().cuda()
+    lib = _lib.load()
+    old = lib.vt_set_option(b"smalln_is", mode)
+    try:
+        y = ops.smalln_conv(ops.to_nhwc(x.cuda()), wp, ops.conv_taps(3, 1), 3, B, H, W, planar=pl.cuda(), planar_weight=wpl,
+                            bias=b.cuda(), src_mask=m.cuda())
+    finally:
+        lib.vt_set_option(b"smalln_is", old)
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    assert maxerr(y.cpu(), ref) <= 2e-5

@@ -34,7 +34,7 @@ class ConvDesc(Structure):
         ("round_tf32", c_int32), ("reserved", c_int32),
         ("rgb_w", c_void_p), ("rgb_bias", c_void_p), ("rgb_skip", c_void_p), ("rgb_skip_kernel", c_void_p),
         ("rgb_out", c_void_p),
-        ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p),
+        ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("src_scale", c_void_p * 2),
     ]
 
 
@@ -51,7 +51,7 @@ class SmallNDesc(Structure):
         ("skip", c_void_p), ("skip_kernel", c_void_p),
         ("out", c_void_p), ("mul_out", c_void_p), ("mul_src", c_void_p),
         ("mul_c", c_int32), ("round_tf32", c_int32),
-        ("tap_const", c_void_p),
+        ("tap_const", c_void_p), ("src_mask", c_void_p),
     ]
 
 

@@ -15,6 +15,8 @@
 // a transposed stride-2 conv is issued as 4 polyphase calls (tap lists with dy,dx in {0,-1}) into a strided view.
 #include "common.cuh"
 
+int g_smalln_is = 1;   // input-stationary kernel for 3x3 small-N convolutions: 1 = where measured faster, 2 = always, 0 = never
+
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -123,6 +125,79 @@ struct SmallNArgs {
   vt_smalln_desc d;
 };
 
+// Per-pixel tail shared by both small-N kernels: lane L <-> pixel (y, x0 + L) of batch image b; `keep[n]` holds the NHWC-source
+// part of the convolution.  Adds the planar-source taps, bias, activation, the up-sampled skip, stores planar outputs and (optionally)
+// writes mul_src * out[:,0] for the whole warp row.  Must be called by all 32 lanes.
+template <int N>
+__device__ __forceinline__ void smalln_pixel_epilogue(const vt_smalln_desc& d, int b, int y, int x0, bool row_ok, float (&keep)[N],
+                                                      const float* Wp, const float* Ks) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  const int grp = lane >> 3;
+  const int64_t HW = (int64_t)d.H * d.W;
+  const int hs = d.H / 2, ws = d.W / 2;
+  // ---- per-pixel epilogue: lane L <-> pixel (y, x0 + L)
+  const int x = x0 + lane;
+  const bool p_ok = row_ok && x < d.W;
+  const int64_t p = (int64_t)y * d.W + x;
+  float m0v = 0.f;
+  if (p_ok) {
+    if (d.n_planar > 0) {
+      for (int t = 0; t < d.taps; ++t) {
+        const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+        if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+        for (int cp = 0; cp < d.n_planar; ++cp) {
+          const float a = __ldg(d.planar + ((int64_t)b * d.n_planar + cp) * HW + (int64_t)iy * d.W + ix);
+#pragma unroll
+          for (int n = 0; n < N; ++n) keep[n] = fmaf(a, Wp[(t * N + n) * d.n_planar + cp], keep[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float v = keep[n];
+      if (d.bias) v += d.bias[n];
+      if (d.act == VT_ACT_RELU_TANH) v = tanhf(fmaxf(v, 0.f));
+      if (d.skip) {
+        // upfirdn2d(skip, k, up=2, down=1, pad=(2,1)) at (y, x): taps with (y - 2 + ky) even
+        const float* sp = d.skip + ((int64_t)b * N + n) * (int64_t)hs * ws;
+        float u = 0.f;
+        const int ty = y - 2, tx = x - 2;
+        for (int ky = (ty & 1) ? 1 : 0; ky < 4; ky += 2) {
+          const int iy = (ty + ky) >> 1;  // ty + ky is even; arithmetic shift == floor
+          if (ty + ky < 0 || iy >= hs) continue;
+          for (int kx = (tx & 1) ? 1 : 0; kx < 4; kx += 2) {
+            const int ix = (tx + kx) >> 1;
+            if (tx + kx < 0 || ix >= ws) continue;
+            u = fmaf(__ldg(sp + (int64_t)iy * ws + ix), Ks[(3 - ky) * 4 + (3 - kx)], u);
+          }
+        }
+        v += u;
+      }
+      d.out[((int64_t)b * N + n) * HW + p] = v;
+      if (n == 0) m0v = v;
+    }
+  }
+  if (d.mul_out) {
+    for (int it = 0; it < 8; ++it) {
+      const float m = __shfl_sync(0xffffffffu, m0v, it * 4 + grp);
+      const int xx = x0 + it * 4 + grp;
+      if (row_ok && xx < d.W) {
+        const int64_t pp = (int64_t)y * d.W + xx;
+        const float* ms = d.mul_src + ((int64_t)b * HW + pp) * d.mul_c;
+        float* mo = d.mul_out + ((int64_t)b * HW + pp) * d.mul_c;
+        for (int c = sub * 4; c < d.mul_c; c += 32) {
+          float4 a = __ldg(reinterpret_cast<const float4*>(ms + c));
+          a.x *= m; a.y *= m; a.z *= m; a.w *= m;
+          if (d.round_tf32) { a.x = vt_round_tf32(a.x); a.y = vt_round_tf32(a.y); a.z = vt_round_tf32(a.z); a.w = vt_round_tf32(a.w); }
+          *reinterpret_cast<float4*>(mo + c) = a;
+        }
+      }
+    }
+  }
+
+}
+
 template <int N>
 __global__ void __launch_bounds__(256)
 smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
@@ -197,6 +272,10 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
               const bool ok = ix >= 0 && ix < d.W && (ix - d.tap_dx[t]) < d.W;
               a[it] = ok ? __ldg(reinterpret_cast<const float4*>(d.src + rowo + (int64_t)ix * d.src_cstride))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (d.src_mask && ok) {
+                const float mm = __ldg(d.src_mask + ((int64_t)b * d.H + iy) * d.W + ix);
+                a[it].x *= mm; a[it].y *= mm; a[it].z *= mm; a[it].w *= mm;
+              }
               if (d.src2_mode)
                 e[it] = ok ? __ldg(reinterpret_cast<const float4*>(d.src2 + rowo + (int64_t)ix * d.src_cstride))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -256,65 +335,150 @@ smalln_conv_kernel(const __grid_constant__ SmallNArgs args) {
         }
       }
     }
-    // ---- per-pixel epilogue: lane L <-> pixel (y, x0 + L)
-    const int x = x0 + lane;
-    const bool p_ok = row_ok && x < d.W;
-    const int64_t p = (int64_t)y * d.W + x;
-    float m0v = 0.f;
-    if (p_ok) {
-      if (d.n_planar > 0) {
-        for (int t = 0; t < d.taps; ++t) {
-          const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
-          if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
-          for (int cp = 0; cp < d.n_planar; ++cp) {
-            const float a = __ldg(d.planar + ((int64_t)b * d.n_planar + cp) * HW + (int64_t)iy * d.W + ix);
+    smalln_pixel_epilogue<N>(d, b, y, x0, row_ok, keep, Wp, Ks);
+  }
+}
+
+// ---- input-stationary small-N 3x3 convolution --------------------------------------------------------------------------
+// out[p] = sum_t <x[p + s_t], w_t>.  Instead of gathering 9 shifted pixels per output (9x L1 traffic, and |src - src2| of the
+// virtual concat recomputed 9x), every input pixel of the patch (+1-pixel ring) is read ONCE: its 9*N partial dot products
+// T[r][t][n] = <x[r], w_t[n]> go to shared memory, and each output pixel then sums 9 shifted T entries.  HBM traffic is the
+// input read once (ring overlap 1.2x, served by L2); FMA work is unchanged (9*N*C per pixel).
+// Block = 8 warps, output patch 16 rows x 32 columns; phase 1 walks the (16+2)x(32+2) region 4*IT pixels per warp step
+// (8 lanes x float4 = one pixel's 32-channel chunk), phase 2 maps lane <-> column like smalln_conv_kernel.
+constexpr int IS_TAPS = 9, IS_PH = 16, IS_PW = 32;
+
+template <int N, int IT>
+__global__ void __launch_bounds__(256)
+smalln_is_kernel(const __grid_constant__ SmallNArgs args, int dy0, int dy1, int dx0, int dx1, int TS) {
+  const vt_smalln_desc& d = args.d;
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TN = IS_TAPS * N;
+  const int CW = d.src2_mode ? 2 * d.src_c : d.src_c;
+  float* Ws = smem;                                              // [TN][CW]
+  float* Wp = Ws + (size_t)TN * CW;                              // [TN][n_planar]
+  float* Ks = Wp + (size_t)TN * (d.n_planar > 0 ? d.n_planar : 0);
+  float* Tc = Ks + 16;                                           // [TN] per-tap constants (0 if none)
+  float* Ts = Tc + ((TN + 3) & ~3);                              // [RH*RW][TS]
+  const int b = blockIdx.y;
+  const int wb = d.wB > 1 ? b : 0;
+  for (int i = threadIdx.x; i < TN * CW; i += blockDim.x) {
+    const int c = i % CW, tn = i / CW;
+    const int t = tn / N, n = tn % N;
+    Ws[i] = d.weight[(((int64_t)wb * d.w_taps + d.tap_w[t]) * d.Cout + n) * d.w_cstride + c];
+  }
+  if (d.n_planar > 0)
+    for (int i = threadIdx.x; i < TN * d.n_planar; i += blockDim.x) {
+      const int cp = i % d.n_planar, tn = i / d.n_planar;
+      Wp[i] = d.planar_weight[((int64_t)d.tap_w[tn / N] * d.Cout + (tn % N)) * d.n_planar + cp];
+    }
+  if (d.skip && threadIdx.x < 16) Ks[threadIdx.x] = d.skip_kernel[threadIdx.x];
+  for (int i = threadIdx.x; i < TN; i += blockDim.x)
+    Tc[i] = d.tap_const ? d.tap_const[((int64_t)wb * d.w_taps + d.tap_w[i / N]) * d.Cout + (i % N)] : 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3, warp = threadIdx.x >> 5;
+  const int RH = IS_PH + dy1 - dy0, RW = IS_PW + dx1 - dx0, npix = RH * RW;
+  const int patches_x = (d.W + IS_PW - 1) / IS_PW, patches_y = (d.H + IS_PH - 1) / IS_PH;
+  // shifted-sum offsets of the 9 taps inside Ts (phase 2)
+  int toff[IS_TAPS];
 #pragma unroll
-            for (int n = 0; n < N; ++n) keep[n] = fmaf(a, Wp[(t * N + n) * d.n_planar + cp], keep[n]);
+  for (int t = 0; t < IS_TAPS; ++t) toff[t] = ((d.tap_dy[t] - dy0) * RW + (d.tap_dx[t] - dx0)) * TS + t * N;
+
+  for (int patch = blockIdx.x; patch < patches_x * patches_y; patch += gridDim.x) {
+    const int y0 = (patch / patches_x) * IS_PH, x0 = (patch % patches_x) * IS_PW;
+    // ---- phase 1: T[r][t][n] for every input pixel r of the region
+    for (int base = warp * 4 * IT; base < npix; base += 8 * 4 * IT) {
+      const float* pa[IT];
+      const float* pe[IT];
+      bool ok[IT];
+      int rr[IT];
+      float pm[IT];
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int r = base + it * 4 + grp;
+        rr[it] = r;
+        const int ry = r / RW, rx = r - ry * RW;
+        const int iy = y0 + dy0 + ry, ix = x0 + dx0 + rx;
+        ok[it] = r < npix && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+        const int64_t o = ok[it] ? ((((int64_t)b * d.H + iy) * d.W + ix) * d.src_cstride) : 0;
+        pa[it] = d.src + o;
+        pe[it] = d.src2_mode ? d.src2 + o : nullptr;
+        pm[it] = (d.src_mask && ok[it]) ? __ldg(d.src_mask + ((int64_t)b * d.H + iy) * d.W + ix) : 1.f;
+      }
+      float acc[IT][TN];
+#pragma unroll
+      for (int it = 0; it < IT; ++it)
+#pragma unroll
+        for (int tn = 0; tn < TN; ++tn) acc[it][tn] = 0.f;
+      for (int c = sub * 4; c < d.src_c; c += 32) {
+        float4 a[IT], e[IT];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          a[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(pa[it] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (d.src_mask) { a[it].x *= pm[it]; a[it].y *= pm[it]; a[it].z *= pm[it]; a[it].w *= pm[it]; }
+          if (d.src2_mode) e[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(pe[it] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int tn = 0; tn < TN; ++tn) {
+          const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)tn * CW + c);
+#pragma unroll
+          for (int it = 0; it < IT; ++it) {
+            acc[it][tn] = fmaf(a[it].x, w.x, acc[it][tn]);
+            acc[it][tn] = fmaf(a[it].y, w.y, acc[it][tn]);
+            acc[it][tn] = fmaf(a[it].z, w.z, acc[it][tn]);
+            acc[it][tn] = fmaf(a[it].w, w.w, acc[it][tn]);
           }
         }
-      }
+        if (d.src2_mode) {   // second half of the virtual concat: |src - src2|, computed once per pixel
 #pragma unroll
-      for (int n = 0; n < N; ++n) {
-        float v = keep[n];
-        if (d.bias) v += d.bias[n];
-        if (d.act == VT_ACT_RELU_TANH) v = tanhf(fmaxf(v, 0.f));
-        if (d.skip) {
-          // upfirdn2d(skip, k, up=2, down=1, pad=(2,1)) at (y, x): taps with (y - 2 + ky) even
-          const float* sp = d.skip + ((int64_t)b * N + n) * (int64_t)hs * ws;
-          float u = 0.f;
-          const int ty = y - 2, tx = x - 2;
-          for (int ky = (ty & 1) ? 1 : 0; ky < 4; ky += 2) {
-            const int iy = (ty + ky) >> 1;  // ty + ky is even; arithmetic shift == floor
-            if (ty + ky < 0 || iy >= hs) continue;
-            for (int kx = (tx & 1) ? 1 : 0; kx < 4; kx += 2) {
-              const int ix = (tx + kx) >> 1;
-              if (tx + kx < 0 || ix >= ws) continue;
-              u = fmaf(__ldg(sp + (int64_t)iy * ws + ix), Ks[(3 - ky) * 4 + (3 - kx)], u);
+          for (int it = 0; it < IT; ++it) {
+            e[it].x = fabsf(a[it].x - e[it].x); e[it].y = fabsf(a[it].y - e[it].y);
+            e[it].z = fabsf(a[it].z - e[it].z); e[it].w = fabsf(a[it].w - e[it].w);
+          }
+#pragma unroll
+          for (int tn = 0; tn < TN; ++tn) {
+            const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)tn * CW + d.src_c + c);
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+              acc[it][tn] = fmaf(e[it].x, w.x, acc[it][tn]);
+              acc[it][tn] = fmaf(e[it].y, w.y, acc[it][tn]);
+              acc[it][tn] = fmaf(e[it].z, w.z, acc[it][tn]);
+              acc[it][tn] = fmaf(e[it].w, w.w, acc[it][tn]);
             }
           }
-          v += u;
         }
-        d.out[((int64_t)b * N + n) * HW + p] = v;
-        if (n == 0) m0v = v;
       }
-    }
-    if (d.mul_out) {
-      for (int it = 0; it < 8; ++it) {
-        const float m = __shfl_sync(0xffffffffu, m0v, it * 4 + grp);
-        const int xx = x0 + it * 4 + grp;
-        if (row_ok && xx < d.W) {
-          const int64_t pp = (int64_t)y * d.W + xx;
-          const float* ms = d.mul_src + ((int64_t)b * HW + pp) * d.mul_c;
-          float* mo = d.mul_out + ((int64_t)b * HW + pp) * d.mul_c;
-          for (int c = sub * 4; c < d.mul_c; c += 32) {
-            float4 a = __ldg(reinterpret_cast<const float4*>(ms + c));
-            a.x *= m; a.y *= m; a.z *= m; a.w *= m;
-            if (d.round_tf32) { a.x = vt_round_tf32(a.x); a.y = vt_round_tf32(a.y); a.z = vt_round_tf32(a.z); a.w = vt_round_tf32(a.w); }
-            *reinterpret_cast<float4*>(mo + c) = a;
-          }
+      // reduce over the 8 channel-slice lanes; lane (tn & 7) of the pixel's group stores entry tn
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+#pragma unroll
+        for (int tn = 0; tn < TN; ++tn) {
+          float v = acc[it][tn];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          if ((tn & 7) == sub && rr[it] < npix) Ts[(size_t)rr[it] * TS + tn] = ok[it] ? v + Tc[tn] : 0.f;
         }
       }
     }
+    __syncthreads();
+    // ---- phase 2: shifted sum + per-pixel tail; warp w owns rows w and w + 8 of the patch
+#pragma unroll
+    for (int h = 0; h < IS_PH / 8; ++h) {
+      const int ly = warp + 8 * h, y = y0 + ly;
+      const bool row_ok = y < d.H;
+      float keep[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) keep[n] = 0.f;
+      const float* tp = Ts + (size_t)(ly * RW + lane) * TS;
+#pragma unroll
+      for (int t = 0; t < IS_TAPS; ++t)
+#pragma unroll
+        for (int n = 0; n < N; ++n) keep[n] += tp[toff[t] + n];
+      smalln_pixel_epilogue<N>(d, b, y, x0, row_ok, keep, Wp, Ks);
+    }
+    __syncthreads();
   }
 }
 
@@ -389,6 +553,7 @@ extern "C" int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream) {
   if (validate_conv_desc(d, "conv2d_direct")) return 1;
   VT_CHECK(d->B <= 65535 && vt_cdiv(d->Cout, BN) <= 65535, "conv2d_direct: grid too large");
   VT_CHECK(!d->rgb_w, "conv2d_direct: the fused ToRGB tail exists only in the tensor-core kernel");
+  VT_CHECK(!d->src_scale[0] && !d->src_scale[1], "conv2d_direct: src_scale is only implemented by the bf16x3 tensor-core kernel");
   const int64_t HoWo = (int64_t)d->Ho * d->Wo;
   dim3 grid((unsigned)vt_cdiv(HoWo, BM), (unsigned)vt_cdiv(d->Cout, BN), (unsigned)d->B);
   for (int ph = 0; ph < d->n_phase; ++ph) {   // one launch per output phase (weight rows ph*Cout.., view offset phase_off[ph])
@@ -420,6 +585,7 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   VT_CHECK(d->weight || d->src_c == 0, "smalln_conv: null weight");
   VT_CHECK(d->act == VT_ACT_NONE || d->act == VT_ACT_RELU_TANH, "smalln_conv: bad act");
   VT_CHECK(d->out != nullptr, "smalln_conv: null out");
+  VT_CHECK(!d->src_mask || !d->src2_mode, "smalln_conv: src_mask cannot be combined with the virtual concat");
   if (d->skip) VT_CHECK(d->skip_kernel && d->H % 2 == 0 && d->W % 2 == 0, "smalln_conv: skip needs a 4x4 kernel and even H, W");
   if (d->mul_out) VT_CHECK(d->mul_src && d->mul_c % 4 == 0 && aligned16(d->mul_src) && aligned16(d->mul_out), "smalln_conv: bad mul_out args");
   for (int t = 0; t < d->taps; ++t) VT_CHECK(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "smalln_conv: tap_w out of range");
@@ -428,6 +594,42 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   a.d = *d;
   const int cw = d->src2_mode ? 2 * d->src_c : d->src_c;
   VT_CHECK(d->src_c == 0 || d->w_cstride >= cw, "smalln_conv: weight row shorter than the (virtual-concat) channel count");
+  cudaStream_t st = (cudaStream_t)stream;
+  // input-stationary kernel for 9-tap convolutions whose taps stay within +-2 pixels
+  // (measured on B200: faster than the gather kernel for Cout == 1 once there are >= 2 patches per SM, slower for Cout >= 2)
+  const bool is_auto = d->Cout == 1 && vt_cdiv(d->W, IS_PW) * vt_cdiv(d->H, IS_PH) * d->B >= 2 * (int64_t)vt_num_sms();
+  if ((g_smalln_is == 2 || (g_smalln_is == 1 && is_auto)) && d->taps == IS_TAPS && d->src_c >= 32) {
+    int dy0 = 0, dy1 = 0, dx0 = 0, dx1 = 0;
+    for (int t = 0; t < d->taps; ++t) {
+      dy0 = d->tap_dy[t] < dy0 ? d->tap_dy[t] : dy0; dy1 = d->tap_dy[t] > dy1 ? d->tap_dy[t] : dy1;
+      dx0 = d->tap_dx[t] < dx0 ? d->tap_dx[t] : dx0; dx1 = d->tap_dx[t] > dx1 ? d->tap_dx[t] : dx1;
+    }
+    const int tn = IS_TAPS * d->Cout;
+    const int TS = tn | 1;   // odd pixel stride in Ts: conflict-free column-wise reads
+    const int RH = IS_PH + dy1 - dy0, RW = IS_PW + dx1 - dx0;
+    const size_t smem_is = ((size_t)tn * (cw + d->n_planar) + 16 + ((tn + 3) & ~3) + (size_t)RH * RW * TS) * sizeof(float);
+    if (dy1 - dy0 <= 4 && dx1 - dx0 <= 4 && smem_is <= 200 * 1024) {
+      int64_t blocks = vt_cdiv(d->W, IS_PW) * vt_cdiv(d->H, IS_PH);
+      const int64_t cap = vt_cdiv((int64_t)vt_num_sms() * 3, d->B);
+      if (blocks > cap) blocks = cap;
+      dim3 grid((unsigned)blocks, (unsigned)d->B);
+#define VT_LAUNCH_IS(NN, ITT)                                                                                          \
+  do {                                                                                                                 \
+    if (smem_is > 48 * 1024)                                                                                           \
+      VT_CUDA(cudaFuncSetAttribute(smalln_is_kernel<NN, ITT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_is)); \
+    smalln_is_kernel<NN, ITT><<<grid, 256, smem_is, st>>>(a, dy0, dy1, dx0, dx1, TS);                                    \
+  } while (0)
+      switch (d->Cout) {
+        case 1: VT_LAUNCH_IS(1, 4); break;
+        case 2: VT_LAUNCH_IS(2, 2); break;
+        case 3: VT_LAUNCH_IS(3, 2); break;
+        default: VT_LAUNCH_IS(4, 1); break;
+      }
+#undef VT_LAUNCH_IS
+      VT_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const size_t smem = ((size_t)d->taps * d->Cout * (cw + d->n_planar + 1) + 16) * sizeof(float);
   VT_CHECK(smem <= 200 * 1024, "smalln_conv: weights (%zu B) do not fit in shared memory", smem);
   const int64_t HW = (int64_t)d->H * d->W;
@@ -435,7 +637,6 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   const int64_t cap = (int64_t)vt_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)d->B);
-  cudaStream_t st = (cudaStream_t)stream;
 #define VT_LAUNCH_SMALLN(NN)                                                                                   \
   do {                                                                                                         \
     if (smem > 48 * 1024)                                                                                      \

@@ -28,6 +28,7 @@ using namespace vt_tc;
 
 int vt_validate_conv_desc(const vt_conv_desc* d, const char* who);
 extern int g_upfirdn_tiled;
+extern int g_smalln_is;
 
 namespace {
 
@@ -66,6 +67,9 @@ struct TcArgs {
   // fused ToRGB tail
   const float* rgb_w; const float* rgb_bias; const float* rgb_skip; const float* rgb_skip_kernel; float* rgb_out;
   const float* slope_vec;
+  const float* src_scale[2]; // bf16x3: optional planar per-pixel multiplier of source s (kernel-space strides below)
+  int64_t sc_sb, sc_sy, sc_sx;
+  int in_w, in_h;            // kernel-space input extents
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
   int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
 };
@@ -296,13 +300,19 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     const int rows = p.a_tx_bytes >> 7;
     int a_st = 0;
     uint32_t a_par = 0;
+    const int bw = p.halo ? p.halo_w : TILE_W;   // pixels per box row
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
+      const int m = tile % m_tiles;
+      const int b = m / tiles_per_img, rem = m % tiles_per_img;
+      const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       for (int s = 0; s < p.n_src; ++s) {
+        const float* sc = p.src_scale[s];
         for (int kc = 0; kc < p.kchunks[s]; ++kc) {
           const int loads = p.halo ? 1 : p.n_steps;
           for (int l = 0; l < loads; ++l) {
             VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 9));
             const uint32_t stage = a_base + a_st * p.a_stage_bytes;
+            const int bx0 = ox0 + (p.halo ? p.halo_x0 : p.step_vx[l]), by0 = oy0 + (p.halo ? p.halo_y0 : p.step_vy[l]);
             for (int r = t; r < rows; r += 64) {
               const uint32_t row = stage + (uint32_t)r * 128u;
               const uint32_t ph = (row >> 7) & 7u;
@@ -312,6 +322,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 float4 v;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(row + ((j ^ ph) << 4)));
                 f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+              }
+              if (sc) {   // per-pixel multiplier of this source (f_E * m_E): rows are box pixels in raster order
+                const int ry = r / bw, rx = r - ry * bw;
+                const int ix = bx0 + rx, iy = by0 + ry;
+                const float mm = (ix >= 0 && ix < p.in_w && iy >= 0 && iy < p.in_h)
+                                     ? __ldg(sc + (int64_t)b * p.sc_sb + (int64_t)iy * p.sc_sy + (int64_t)ix * p.sc_sx) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] *= mm;
               }
               uint32_t hi[16], lo[16];
 #pragma unroll
@@ -323,9 +341,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
               }
 #pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((m ^ ph) << 4)), "r"(hi[4 * m]), "r"(hi[4 * m + 1]), "r"(hi[4 * m + 2]), "r"(hi[4 * m + 3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((m + 4) ^ ph) << 4)), "r"(lo[4 * m]), "r"(lo[4 * m + 1]), "r"(lo[4 * m + 2]), "r"(lo[4 * m + 3]) : "memory");
+              for (int m4 = 0; m4 < 4; ++m4) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((m4 ^ ph) << 4)), "r"(hi[4 * m4]), "r"(hi[4 * m4 + 1]), "r"(hi[4 * m4 + 2]), "r"(hi[4 * m4 + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((m4 + 4) ^ ph) << 4)), "r"(lo[4 * m4]), "r"(lo[4 * m4 + 1]), "r"(lo[4 * m4 + 2]), "r"(lo[4 * m4 + 3]) : "memory");
               }
             }
             fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -586,6 +604,7 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(d->out_sx % 4 == 0 && d->out_sy % 4 == 0 && d->out_sb % 4 == 0, "conv_tc: output strides must be multiples of 4 floats");
   VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
+  VT_SUP((!d->src_scale[0] && !d->src_scale[1]) || (d->weight_bf16x3 && d->stride == 1), "conv_tc: src_scale needs the bf16x3 mode and stride 1");
   VT_SUP(!d->weight_bf16x3 || d->w_cstride % KCH == 0, "conv_tc: bf16x3 weights need a channel stride that is a multiple of 32");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
   VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
@@ -606,6 +625,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
   if (key && strcmp(key, "tc_transpose") == 0) { int old = g_tc_transpose; g_tc_transpose = value; return old; }
   if (key && strcmp(key, "tc_pair_y") == 0) { int old = g_tc_pair_y; g_tc_pair_y = value; return old; }
+  if (key && strcmp(key, "smalln_is") == 0) { int old = g_smalln_is; g_smalln_is = value; return old; }
   if (key && strcmp(key, "upfirdn_tiled") == 0) { int old = g_upfirdn_tiled; g_upfirdn_tiled = value; return old; }
   return -1;
 }
@@ -655,6 +675,9 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;
   a.bf16x3 = d->weight_bf16x3 != nullptr;
+  a.src_scale[0] = d->src_scale[0]; a.src_scale[1] = d->src_scale[1];
+  a.in_w = gW; a.in_h = gH;
+  a.sc_sb = (int64_t)d->H * d->W; a.sc_sy = T ? 1 : d->W; a.sc_sx = T ? d->W : 1;
 
   // ---- K iteration space
   a.n_src = d->n_src;

@@ -38,7 +38,18 @@ def get_precision() -> str:
 
 
 # algorithm switches (kept so tests can compare both formulations on the GPU)
-_options = {"fold_upconv": True, "fuse_torgb": True}
+# fold_upconv: True = always fold Blur o conv_transpose into one N = 4*Cout convolution; an int = only when Cin <= that value
+# (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 256, slower at Cin = 512:
+# tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
+import os as _os
+_options = {"fold_upconv": 256, "fuse_torgb": True, "fuse_mask_mul": True}
+if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
+    _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
+
+
+def use_folded_upconv(cin: int) -> bool:
+    v = _options["fold_upconv"]
+    return bool(v) if isinstance(v, bool) else cin <= int(v)
 
 
 def set_option(name: str, value) -> None:
@@ -226,7 +237,7 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 noise_w: Optional[torch.Tensor] = None, act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0,
                 res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
                 precision: Optional[str] = None, rgb: Optional[dict] = None,
-                slope_vec: Optional[torch.Tensor] = None) -> torch.Tensor:
+                slope_vec: Optional[torch.Tensor] = None, src_scale: Optional[Sequence] = None) -> torch.Tensor:
     """General NHWC convolution (virtual channel-concat of ``srcs``).
 
     ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
@@ -294,8 +305,19 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
         d.rgb_w, d.rgb_bias, d.rgb_out = rgb["w"].data_ptr(), rgb["bias"].data_ptr(), rgb_out.data_ptr()
         if rgb.get("skip") is not None:
             d.rgb_skip, d.rgb_skip_kernel = rgb["skip"].contiguous().data_ptr(), rgb["kernel"].contiguous().data_ptr()
+    if src_scale is not None:
+        # per-pixel planar [B,H,W] multiplier of a source (bf16x3 tensor-core mode only; see scale_fusable)
+        for i, sc in enumerate(src_scale):
+            if sc is not None:
+                _req_cuda(sc)
+                if sc.numel() != B * H * W or not sc.is_contiguous():
+                    raise _lib.VtError("conv2d_nhwc: src_scale must be a contiguous [B,H,W] map")
+                d.src_scale[i] = sc.data_ptr()
     lib = _lib.load()
+    if prec == "bf16x3":
+        d.weight_bf16x3 = 1   # placeholder so that vt_conv2d_tc_supported sees the mode; replaced below
     use_tc = prec in ("tf32", "bf16x3") and lib.vt_conv2d_tc_supported(d)
+    d.weight_bf16x3 = None
     if use_tc and prec == "bf16x3":
         d.weight_bf16x3 = split_weights_bf16x3(weight).data_ptr()
     if use_tc:
@@ -330,6 +352,11 @@ def split_weights_bf16x3(weight: torch.Tensor) -> torch.Tensor:
                                              weight.shape[-1], _stream()))
     weight._vt_bf16x3 = (ver, weight.data_ptr(), out)
     return out
+
+
+def scale_fusable(precision: Optional[str] = None) -> bool:
+    """conv2d_nhwc(src_scale=...) is available (the split-operand tensor-core mode applies it while converting tiles)."""
+    return (precision or _precision) == "bf16x3" and _options["fuse_mask_mul"]
 
 
 def rgb_fusable(Cout: int, precision: Optional[str] = None) -> bool:
@@ -412,7 +439,8 @@ def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], tap
                 planar: Optional[torch.Tensor] = None, planar_weight: Optional[torch.Tensor] = None,
                 bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, skip: Optional[torch.Tensor] = None,
                 skip_kernel: Optional[torch.Tensor] = None, mul_src: Optional[torch.Tensor] = None,
-                src2: Optional[torch.Tensor] = None, tap_const: Optional[torch.Tensor] = None):
+                src2: Optional[torch.Tensor] = None, tap_const: Optional[torch.Tensor] = None,
+                src_mask: Optional[torch.Tensor] = None):
     """Cout<=4 convolution with planar NCHW output ``[B,Cout,H,W]``; optionally also returns ``mul_src * out[:,0]``.
     ``src2``: the input is the virtual concat ``[src | abs(src - src2)]`` (weight rows hold 2*C channels);
     ``tap_const`` ``[wB, w_taps, Cout]``: constant added for every in-bounds tap (folded AdaIN affine)."""
@@ -437,6 +465,11 @@ def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], tap
             d.src2, d.src2_mode = src2.data_ptr(), 1
         if tap_const is not None:
             d.tap_const = tap_const.contiguous().data_ptr()
+        if src_mask is not None:
+            _req_cuda(src_mask)
+            if src_mask.numel() != B * H * W or not src_mask.is_contiguous():
+                raise _lib.VtError("smalln_conv: src_mask must be a contiguous [B,H,W] map")
+            d.src_mask = src_mask.data_ptr()
     else:
         d.wB, d.w_taps = 1, (planar_weight.shape[0] if planar_weight is not None else 1)
     d.Cout = Cout

@@ -203,7 +203,7 @@ class ModulatedConv2d(nn.Module):
         if self.upsample:
             if k != 3:
                 raise NotImplementedError("upsampling ModulatedConv2d is 3x3 in StyleGAN2")
-            if tuple(self.blur.kernel.shape) == (4, 4) and tuple(self.blur.pad) == (1, 1) and ops.get_option("fold_upconv"):
+            if tuple(self.blur.kernel.shape) == (4, 4) and tuple(self.blur.pad) == (1, 1) and ops.use_folded_upconv(self.in_channel):
                 # Blur o conv_transpose folded into 4 phase-specific 3x3 kernels: one launch, no intermediate tensor
                 w9 = self.modulated_weights(style, Cs, externalweight, round_tf32=False)
                 wf = ops.fold_upconv_weights(w9, self.blur.kernel)

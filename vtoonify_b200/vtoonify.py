@@ -38,8 +38,8 @@ class Conv2d(nn.Module):
         self._w = _PreppedWeight()
         self._wp = _PreppedWeight()
 
-    def forward_nhwc(self, x, act=ACT_NONE, slope=0.2, gain=1.0, res=None, alpha=1.0, beta=1.0, x2=None):
-        """x (and optional second concat source x2) NHWC -> NHWC."""
+    def forward_nhwc(self, x, act=ACT_NONE, slope=0.2, gain=1.0, res=None, alpha=1.0, beta=1.0, x2=None, x2_scale=None):
+        """x (and optional second concat source x2, optionally multiplied per pixel by the planar map x2_scale) NHWC -> NHWC."""
         B, H, W, Cs = x.shape
         k = self.kernel_size
         cin = Cs + (0 if x2 is None else x2.shape[3])
@@ -48,9 +48,10 @@ class Conv2d(nn.Module):
         Wo = ops.conv_out_size(W, k, self.stride, self.padding, 1)
         srcs = [x] if x2 is None else [x, x2]
         return ops.conv2d_nhwc(srcs, w, ops.conv_taps(k, self.padding), self.stride, Ho, Wo, bias=self.bias, act=act,
-                               slope=slope, gain=gain, res=res, alpha=alpha, beta=beta)
+                               slope=slope, gain=gain, res=res, alpha=alpha, beta=beta,
+                               src_scale=None if x2_scale is None else [None, x2_scale])
 
-    def forward_smalln(self, x, planar=None, act=ACT_NONE, mul_src=None):
+    def forward_smalln(self, x, planar=None, act=ACT_NONE, mul_src=None, src_mask=None):
         """Cout <= 4 form: input channels = [planar (NCHW, first) | x (NHWC)] -> planar NCHW output."""
         B, H, W, Cs = x.shape
         k = self.kernel_size
@@ -63,7 +64,7 @@ class Conv2d(nn.Module):
             self._split_key = key
         w = self._wp.get(self._w_nhwc_part, 1.0, Cs, round_tf32=False)
         return ops.smalln_conv(x, w, ops.conv_taps(k, self.padding), self.weight.shape[0], B, H, W, planar=planar,
-                               planar_weight=self._w_planar, bias=self.bias, act=act, mul_src=mul_src)
+                               planar_weight=self._w_planar, bias=self.bias, act=act, mul_src=mul_src, src_mask=src_mask)
 
     def forward(self, input):
         C = input.shape[1]
@@ -139,6 +140,12 @@ class Fusion(nn.Module):
         w_plain = self.conv2._wp.get(self.conv2.weight, 1.0, C2, round_tf32=False)          # [1, 9, 1, 2C]
         w_fold, k_fold = ops.affine_fold_weights(w_plain, stats, gb)
         B, H, W, _ = f_G.shape
+        if ops.scale_fusable():
+            # f_E * m_E (model/vtoonify.py:127) is never written: the fusion conv multiplies f_E tiles by m_E while it splits
+            # them for the tensor cores, and fusion_skip's 3-channel conv scales its loads (VToonify.forward)
+            m_E = ops.smalln_conv(f_G, w_fold, ops.conv_taps(3, 1), 1, B, H, W, bias=self.conv2.bias, act=ACT_RELU_TANH,
+                                  src2=f_E, tap_const=k_fold)
+            return self.conv.forward_nhwc(f_G, x2=f_E, x2_scale=m_E), m_E, None
         m_E, fEm = ops.smalln_conv(f_G, w_fold, ops.conv_taps(3, 1), 1, B, H, W, bias=self.conv2.bias, act=ACT_RELU_TANH,
                                    mul_src=f_E, src2=f_E, tap_const=k_fold)
         f_out = self.conv.forward_nhwc(f_G, x2=fEm)
@@ -245,7 +252,10 @@ class VToonify(nn.Module):
                 f_E = encoder_features[fi]
                 if D:
                     out, m_E, fEm = self.fusion_out[fi].forward_nhwc(out, f_E, d_s)
-                    skip = self.fusion_skip[fi].forward_smalln(fEm, planar=skip)
+                    if fEm is None:
+                        skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip, src_mask=m_E)
+                    else:
+                        skip = self.fusion_skip[fi].forward_smalln(fEm, planar=skip)
                     m_Es.append(m_E)
                 else:
                     out = self.fusion_out[fi].forward_nhwc(out, x2=f_E)

@@ -187,6 +187,9 @@ typedef struct vt_smalln_desc {
   int32_t mul_c, round_tf32;
   const float* tap_const;       /* optional [wB][w_taps][Cout]: constant added per in-bounds tap (folded affine) */
   const float* src_mask;        /* optional planar [B,H,W]: the NHWC source is multiplied per pixel by it (f_E * m_E)        */
+  const float* tsum;            /* optional NHWC [B,H,W,tsum_c] tensor of per-tap partial products T[.., t*Cout + n] computed by a
+                                 * 1x1 tensor-core convolution: out[n] += sum over in-bounds taps t of T[p + shift_t][t*Cout + n]  */
+  int32_t tsum_c, reserved;
 } vt_smalln_desc;
 int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream);
 /* Fold a per-(b,c) affine (AdaIN: gamma*(x-mean)*rstd+beta, model/dualstylegan.py:16-21) into conv weights:

@@ -470,3 +470,33 @@ def test_smalln_masked_source(mode):
         lib.vt_set_option(b"smalln_is", old)
         ops.set_precision(ops.DEFAULT_PRECISION)
     assert maxerr(y.cpu(), ref) <= 2e-5
+
+
+@pytest.mark.parametrize("with_planar,with_mask", [(True, True), (True, False), (False, False)])
+def test_smalln_conv_via_tensor_core_tap_products(with_planar, with_mask):
+    """Conv2d.forward_smalln in the bf16x3 mode: 1x1 tensor-core conv producing the 27 per-tap partial products + shifted sum,
+    against torch and against the gather kernel."""
+    from vtoonify_b200 import ops
+    from vtoonify_b200.vtoonify import Conv2d
+    g = torch.Generator().manual_seed(29)
+    B, C, H, W = 2, 64, 21, 37
+    npl = 3 if with_planar else 0
+    conv = Conv2d(C + npl, 3, 3, 1, 1, bias=True)
+    conv.weight.data = torch.randn(conv.weight.shape, generator=g) / 24
+    conv.bias.data = torch.randn(3, generator=g)
+    x = torch.randn((B, C, H, W), generator=g); m = torch.rand((B, 1, H, W), generator=g)
+    pl = torch.randn((B, 3, H, W), generator=g) if with_planar else None
+    xin = x * m if with_mask else x
+    ref = F.conv2d(torch.cat([pl, xin], 1) if with_planar else xin, conv.weight.data, conv.bias.data, padding=1)
+    conv.cuda()
+    ops.set_precision("bf16x3")
+    try:
+        kw = dict(planar=pl.cuda() if with_planar else None, src_mask=m.cuda() if with_mask else None)
+        y_tc = conv.forward_smalln(ops.to_nhwc(x.cuda()), **kw)
+        ops.set_option("smalln_via_tc", False)
+        y_g = conv.forward_smalln(ops.to_nhwc(x.cuda()), **kw)
+    finally:
+        ops.set_option("smalln_via_tc", True)
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    assert maxerr(y_g.cpu(), ref) <= 2e-5
+    assert maxerr(y_tc.cpu(), ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())

@@ -58,3 +58,5 @@ with torch.no_grad():
     up_case(4, 128, 64, 576, 1024)
     up_case(4, 512, 256, 144, 256)
     conv_case(4, 256, 128, 576, 1024)
+    conv_case(4, 128, 32, 576, 1024, k=1)
+    conv_case(4, 128, 256, 288, 512, k=3)

@@ -51,7 +51,7 @@ class SmallNDesc(Structure):
         ("skip", c_void_p), ("skip_kernel", c_void_p),
         ("out", c_void_p), ("mul_out", c_void_p), ("mul_src", c_void_p),
         ("mul_c", c_int32), ("round_tf32", c_int32),
-        ("tap_const", c_void_p), ("src_mask", c_void_p),
+        ("tap_const", c_void_p), ("src_mask", c_void_p), ("tsum", c_void_p), ("tsum_c", c_int32), ("reserved", c_int32),
     ]
 
 

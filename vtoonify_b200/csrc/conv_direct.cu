@@ -142,12 +142,54 @@ __device__ __forceinline__ void smalln_pixel_epilogue(const vt_smalln_desc& d, i
   const int64_t p = (int64_t)y * d.W + x;
   float m0v = 0.f;
   if (p_ok) {
-    if (d.n_planar > 0) {
-      for (int t = 0; t < d.taps; ++t) {
+    // Both tap loops are written branch-free (clamped address, 0/1 weight) over a compile-time 9 taps so that all loads of a
+    // pixel are in flight together; this tail runs once per pixel with little other work to hide a serial chain of L2 latencies.
+    if (d.tsum) {   // shifted sum of per-tap partial products (1x1 tensor-core conv output)
+      float tv[9][N];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int tt = t < d.taps ? t : 0;
+        const int iy = y + d.tap_dy[tt], ix = x + d.tap_dx[tt];
+        const bool ok = t < d.taps && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+        const int cy = ok ? iy : y, cx = ok ? ix : x;
+        const float* tp = d.tsum + (((int64_t)b * d.H + cy) * d.W + cx) * d.tsum_c + tt * N;
+#pragma unroll
+        for (int n = 0; n < N; ++n) tv[t][n] = ok ? __ldg(tp + n) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int n = 0; n < N; ++n) keep[n] += tv[t][n];
+      for (int t = 9; t < d.taps; ++t) {
         const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
         if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
-        for (int cp = 0; cp < d.n_planar; ++cp) {
-          const float a = __ldg(d.planar + ((int64_t)b * d.n_planar + cp) * HW + (int64_t)iy * d.W + ix);
+        const float* tp = d.tsum + (((int64_t)b * d.H + iy) * d.W + ix) * d.tsum_c + t * N;
+#pragma unroll
+        for (int n = 0; n < N; ++n) keep[n] += __ldg(tp + n);
+      }
+    }
+    if (d.n_planar > 0) {
+      for (int cp = 0; cp < d.n_planar; ++cp) {
+        const float* pp = d.planar + ((int64_t)b * d.n_planar + cp) * HW;
+        float av[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int tt = t < d.taps ? t : 0;
+          const int iy = y + d.tap_dy[tt], ix = x + d.tap_dx[tt];
+          const bool ok = t < d.taps && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+          av[t] = ok ? __ldg(pp + (int64_t)iy * d.W + ix) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (t < d.taps) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) keep[n] = fmaf(av[t], Wp[(t * N + n) * d.n_planar + cp], keep[n]);
+          }
+        }
+        for (int t = 9; t < d.taps; ++t) {
+          const int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+          if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+          const float a = __ldg(pp + (int64_t)iy * d.W + ix);
 #pragma unroll
           for (int n = 0; n < N; ++n) keep[n] = fmaf(a, Wp[(t * N + n) * d.n_planar + cp], keep[n]);
         }
@@ -585,6 +627,7 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   VT_CHECK(d->weight || d->src_c == 0, "smalln_conv: null weight");
   VT_CHECK(d->act == VT_ACT_NONE || d->act == VT_ACT_RELU_TANH, "smalln_conv: bad act");
   VT_CHECK(d->out != nullptr, "smalln_conv: null out");
+  VT_CHECK(!d->tsum || d->tsum_c >= d->taps * d->Cout, "smalln_conv: tsum_c must hold taps*Cout partial products");
   VT_CHECK(!d->src_mask || !d->src2_mode, "smalln_conv: src_mask cannot be combined with the virtual concat");
   if (d->skip) VT_CHECK(d->skip_kernel && d->H % 2 == 0 && d->W % 2 == 0, "smalln_conv: skip needs a 4x4 kernel and even H, W");
   if (d->mul_out) VT_CHECK(d->mul_src && d->mul_c % 4 == 0 && aligned16(d->mul_src) && aligned16(d->mul_out), "smalln_conv: bad mul_out args");

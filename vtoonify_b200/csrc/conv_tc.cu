@@ -51,7 +51,10 @@ struct TcArgs {
                                                // dimension is phase-major [n_phase][Cout] (folded up-conv), else 1
   int tgroup;                                  // taps per weight TMA box / pipeline step (consecutive slabs)
   int grp_first_mask, grp_last_mask;           // bit t: tap t is the first / last of its weight box (n_steps <= 32)
-  int halo, halo_x0, halo_y0, halo_w;
+  int halo, halo_x0, halo_y0, halo_w;   // halo staging; x0/y0/w describe view 0's box (stride 1: the only one)
+  // halo boxes of one K chunk: stride 1 has one, stride 2 one per parity view in use (each with its own extent and pitch)
+  int n_hv, hv_view[4], hv_x0[4], hv_y0[4], hv_off[4], hv_bytes[4], a_rows;
+  uint16_t step_sbo[VT_MAX_TAPS];   // halo mode: stride (bytes) between 8-pixel row groups of the tap's box
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   int block_n, n_tiles, tiles_x, tiles_y, B, total_tiles, tmem_cols;
   int Ho, Wo, Cout, wB, out_cpitch;
@@ -79,8 +82,12 @@ struct TcArgs {
 // CG = 1: one CTA per work item (M = 128).  CG = 2: a CTA pair (cluster of 2) shares one tcgen05.mma.cta_group::2 with
 // M = 256: each CTA stages the activations of its own 128 pixels and HALF of every weight tile, so per-SM shared-memory
 // traffic (TMA writes + tensor-core operand reads) drops from ~160 to ~100 B/clk; rank 0 issues the MMAs for both.
+// warps: 0 TMA producer, 1 MMA issuer, 2-3 and 8-9 operand transform (bf16x3), 2 also TMEM alloc, 4-7 epilogue
+constexpr int TC_THREADS = 320;
+constexpr int XFORM_WARPS = 4;
+
 template <int CG>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -114,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     for (int ph = 0; ph < p.n_phase; ++ph) tma_prefetch_desc(&p.out_map[ph]);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); mbar_init(a_ready(i), 2 * CG); }
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); mbar_init(a_ready(i), XFORM_WARPS * CG); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4 * CG); }
     fence_barrier_init();
@@ -157,12 +164,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           if (p.halo) {
             VT_TWAIT(0, mbar_wait(a_empty(a_st), a_par ^ 1, 1));
             if (elect_one()) {
+              const uint32_t st = a_base + a_st * p.a_stage_bytes;
               if (CG == 2 && !p.bf16x3) {
                 if (rank == 0) mbar_arrive_expect_tx(a_full(a_st), 2u * (uint32_t)p.a_tx_bytes);
-                tma_load_4d_2sm(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+                for (int v = 0; v < p.n_hv; ++v)
+                  tma_load_4d_2sm(st + p.hv_off[v], &p.in_map[s][p.hv_view[v]], a_full(a_st), c0, ox0 + p.hv_x0[v], oy0 + p.hv_y0[v], b);
               } else {   // (bf16x3: every CTA's transform warps wait on their own a_full)
                 mbar_arrive_expect_tx(a_full(a_st), (uint32_t)p.a_tx_bytes);
-                tma_load_4d(a_base + a_st * p.a_stage_bytes, &p.in_map[s][0], a_full(a_st), c0, ox0 + p.halo_x0, oy0 + p.halo_y0, b);
+                for (int v = 0; v < p.n_hv; ++v)
+                  tma_load_4d(st + p.hv_off[v], &p.in_map[s][p.hv_view[v]], a_full(a_st), c0, ox0 + p.hv_x0[v], oy0 + p.hv_y0[v], b);
               }
             }
             __syncwarp();
@@ -235,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               // same function), so a tap is just a start address shifted by whole 128-byte rows; the descriptor's
               // base-offset field stays 0 (setting it to (addr>>7)&7 was measured WRONG on B200).
               a_addr += (uint32_t)p.step_aoff[j];
-              sbo = (uint32_t)p.halo_w * 128u;
+              sbo = (uint32_t)p.step_sbo[j];
             }
             const uint64_t bdesc = make_smem_desc_sw128(b_base + b_st * p.b_stage_bytes + (uint32_t)gj * tile_bytes_n, 1024, 0);
             const bool last_of_group = (gj == p.tgroup - 1);
@@ -292,12 +302,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       __syncwarp();
       if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
-  } else if ((warp == 2 || warp == 3) && p.bf16x3) {
+  } else if ((warp == 2 || warp == 3 || warp >= 8) && p.bf16x3) {
     // ================= operand transform (bf16x3): fp32 rows -> [hi(32) | lo(32)] bf16 rows, in place =================
     // A 32-channel fp32 row (128 B) becomes the K = 64 bf16 row [a_hi | a_lo] with a_hi = bf16(a), a_lo = bf16(a - a_hi);
     // 16-byte chunk j of the row lives at physical chunk j ^ ((addr >> 7) & 7) (SWIZZLE_128B as TMA wrote it, kept for the MMA).
-    const int t = (warp - 2) * 32 + lane;
-    const int rows = p.a_tx_bytes >> 7;
+    const int t = (warp < 4 ? warp - 2 : warp - 6) * 32 + lane;   // 0 .. 32 * XFORM_WARPS
+    const int rows = p.a_rows;
     int a_st = 0;
     uint32_t a_par = 0;
     const int bw = p.halo ? p.halo_w : TILE_W;   // pixels per box row
@@ -313,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 9));
             const uint32_t stage = a_base + a_st * p.a_stage_bytes;
             const int bx0 = ox0 + (p.halo ? p.halo_x0 : p.step_vx[l]), by0 = oy0 + (p.halo ? p.halo_y0 : p.step_vy[l]);
-            for (int r = t; r < rows; r += 64) {
+            for (int r = t; r < rows; r += 32 * XFORM_WARPS) {
               const uint32_t row = stage + (uint32_t)r * 128u;
               const uint32_t ph = (row >> 7) & 7u;
               float f[32];
@@ -334,11 +344,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
-                hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                // packed converts (one cvt.rn.bf16x2.f32 per pair); a bf16 widened to fp32 is its bits shifted left by 16
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                const float r0 = f[2 * i] - __uint_as_float(hi[i] << 16), r1 = f[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
               }
 #pragma unroll
               for (int m4 = 0; m4 < 4; ++m4) {
@@ -354,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ================= epilogue =================
     const int q = warp - 4;
     const int r = q * 32 + lane;           // accumulator row == pixel index in the M tile
@@ -707,7 +718,9 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   int bn = 256;
   while (bn > 32 && (n_eff % bn) != 0) bn -= 32;
   VT_CHECK(n_eff % bn == 0, "conv_tc: no N tile for N=%d", n_eff);
-  const bool can_halo = (g_tc_mode != 0) && d->stride == 1 && d->taps > 1;
+  // halo staging: multi-tap layers (one box serves all taps) and small-N 1x1 layers (several M tiles per box and weight tile).
+  // tc_mode 3: halo for stride 1 only (A/B tests)
+  const bool can_halo = (g_tc_mode != 0) && (d->taps > 1 || (bn <= 64 && d->stride == 1)) && (d->stride == 1 || g_tc_mode != 3);
   // M tiles per work item: share each weight tile across `mt` pixel tiles when N is small (weights dominate L2->smem
   // traffic there); bounded by TMEM columns and by the halo box fitting a pipeline stage.
   int mt = 1;
@@ -733,7 +746,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   }
   // CTA pairs (cta_group::2, one MMA instruction covers M = 256 pixels): stride-1 halo mode. g_tc_cg2: 1 = every eligible
   // layer (small-N layers are bound by MMA issue, a pair halves the instructions per pixel), 2 = only N tile 256.
-  const int halo1_bytes = (TILE_W + (dxmax - dxmin)) * (TILE_H + (dymax - dymin)) * 128;
+  const int halo1_bytes = d->stride == 1 ? (TILE_W + (dxmax - dxmin)) * (TILE_H + (dymax - dymin)) * 128 : 0;   // (stride 2: decided by the plan below)
   int cg = (g_tc_cg2 && can_halo && (bn == 256 || g_tc_cg2 == 1) && (gWo > TILE_W * mt || gHo > TILE_H) &&
             halo1_bytes <= d->taps * TILE_M * 128 / 2 && halo1_bytes <= 96 * 1024) ? 2 : 1;
   a.tgroup = tgroup;
@@ -741,17 +754,40 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     if (t % tgroup == 0) a.grp_first_mask |= 1 << t;
     if (t % tgroup == tgroup - 1) a.grp_last_mask |= 1 << t;
   }
+  // per parity view (stride 1: view 0 only): offset ranges of the taps that read it
+  int vx0[4], vx1[4], vy0[4], vy1[4];
+  bool vused[4] = {false, false, false, false};
+  for (int t = 0; t < d->taps; ++t) {
+    const int v = a.step_view[t], vx = a.step_vx[t], vy = a.step_vy[t];
+    if (!vused[v]) { vused[v] = true; vx0[v] = vx1[v] = vx; vy0[v] = vy1[v] = vy; }
+    vx0[v] = vx < vx0[v] ? vx : vx0[v]; vx1[v] = vx > vx1[v] ? vx : vx1[v];
+    vy0[v] = vy < vy0[v] ? vy : vy0[v]; vy1[v] = vy > vy1[v] ? vy : vy1[v];
+  }
+  int hv_w[4] = {0, 0, 0, 0}, hv_h[4] = {0, 0, 0, 0};
   for (;; mt /= 2) {
-    const int halo_w = TILE_W * mt + (dxmax - dxmin), halo_h = TILE_H + (dymax - dymin);
-    const int halo_bytes = halo_w * halo_h * 128;
-    a.halo = can_halo && halo_w <= 256 && halo_h <= 256 && halo_bytes <= 96 * 1024 &&
-             (mt > 1 || halo_bytes <= d->taps * TILE_M * 128 / 2);
+    // one halo box per view in use, each 1024-byte aligned inside the stage (the 128B swizzle phase follows address bits 7-9)
+    int halo_bytes = 0, tx_bytes = 0;
+    bool fits = true;
+    a.n_hv = 0;
+    for (int v = 0; v < 4; ++v) {
+      if (!vused[v]) continue;
+      const int w = TILE_W * mt + (vx1[v] - vx0[v]), h = TILE_H + (vy1[v] - vy0[v]);
+      fits = fits && w <= 256 && h <= 256;
+      const int i = a.n_hv++;
+      a.hv_view[i] = v; a.hv_x0[i] = vx0[v]; a.hv_y0[i] = vy0[v]; a.hv_off[i] = halo_bytes; a.hv_bytes[i] = w * h * 128;
+      hv_w[v] = w; hv_h[v] = h;
+      tx_bytes += w * h * 128;
+      halo_bytes = (int)(vt_cdiv(halo_bytes + w * h * 128, 1024) * 1024);
+    }
+    a.halo = can_halo && fits && halo_bytes <= 96 * 1024 && (mt > 1 || tx_bytes <= d->taps * TILE_M * 128 / 2) &&
+             2 * halo_bytes + 2 * (bn / cg) * 128 * tgroup + fixed <= MAX_SMEM;   // at least a 2+2 stage pipeline must fit
     if (!a.halo && mt > 1) continue;
     if (!a.halo) cg = 1;
-    a.halo_x0 = dxmin; a.halo_y0 = dymin; a.halo_w = halo_w;
-    a.a_tx_bytes = a.halo ? halo_bytes : TILE_M * 128;
+    a.halo_x0 = a.hv_x0[0]; a.halo_y0 = a.hv_y0[0]; a.halo_w = hv_w[a.hv_view[0]];
+    a.a_tx_bytes = a.halo ? tx_bytes : TILE_M * 128;
+    a.a_rows = a.halo ? (a.hv_off[a.n_hv - 1] + a.hv_bytes[a.n_hv - 1]) / 128 : TILE_M;
     // shared memory plan: A ring (halo boxes or per-tap tiles) + B ring (weight tiles) + 2 output staging buffers
-    a.a_stage_bytes = (int)(vt_cdiv(a.a_tx_bytes, 1024) * 1024);
+    a.a_stage_bytes = a.halo ? halo_bytes : TILE_M * 128;
     a.b_stage_bytes = (bn / cg) * 128 * tgroup;
     a.a_stages = a.halo ? 3 : 4;
     a.b_stages = tgroup > 1 ? 4 : (cg == 2 ? 8 : 6);
@@ -767,8 +803,13 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.b_tx_bytes = (bn / cg) * 128 * tgroup;
   VT_CHECK(smem_bytes <= MAX_SMEM && a.a_stages >= 2 && a.b_stages >= 2 && a.a_stages <= 8 && a.b_stages <= 8,
            "conv_tc: shared memory plan does not fit (%d B, mt=%d, bn=%d)", smem_bytes, mt, bn);
-  for (int t = 0; t < d->taps; ++t)
-    a.step_aoff[t] = ((a.step_vy[t] - a.halo_y0) * a.halo_w + (a.step_vx[t] - a.halo_x0)) * 128;
+  for (int t = 0; t < d->taps; ++t) {
+    const int v = a.step_view[t];
+    int i = 0;
+    while (i < a.n_hv - 1 && a.hv_view[i] != v) ++i;
+    a.step_aoff[t] = a.hv_off[i] + ((a.step_vy[t] - vy0[v]) * hv_w[v] + (a.step_vx[t] - vx0[v])) * 128;
+    a.step_sbo[t] = (uint16_t)(hv_w[v] * 128);
+  }
   a.mt = mt;
   a.acc_stages = (2 * mt * bn <= 512) ? 2 : 1;
   int tc = 32;
@@ -794,8 +835,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
       const uint64_t real_sx = cs * 4, real_sy = (uint64_t)d->W * cs * 4;
       const uint64_t dims[4] = {cs, (uint64_t)gW, (uint64_t)gH, (uint64_t)d->B};
       const uint64_t str[3] = {T ? real_sy : real_sx, T ? real_sx : real_sy, (uint64_t)d->H * d->W * cs * 4};
-      const uint32_t box[4] = {KCH, (uint32_t)(a.halo ? a.halo_w : TILE_W),
-                               (uint32_t)(a.halo ? TILE_H + (dymax - dymin) : TILE_H), 1};
+      const uint32_t box[4] = {KCH, (uint32_t)(a.halo ? hv_w[0] : TILE_W), (uint32_t)(a.halo ? hv_h[0] : TILE_H), 1};
       if (make_map4(&a.in_map[s][0], d->src[s], dims, str, box, "input")) return 1;
       for (int v = 1; v < 4; ++v) a.in_map[s][v] = a.in_map[s][0];
     } else {
@@ -808,7 +848,8 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
           if (vw < 1 || vh < 1) { if (have0) *mp = a.in_map[s][0]; continue; }
           const uint64_t dims[4] = {cs, (uint64_t)vw, (uint64_t)vh, (uint64_t)d->B};
           const uint64_t str[3] = {2 * cs * 4, 2 * (uint64_t)d->W * cs * 4, (uint64_t)d->H * d->W * cs * 4};
-          const uint32_t box[4] = {KCH, TILE_W, TILE_H, 1};
+          const int v = py * 2 + px;
+          const uint32_t box[4] = {KCH, (uint32_t)((a.halo && vused[v]) ? hv_w[v] : TILE_W), (uint32_t)((a.halo && vused[v]) ? hv_h[v] : TILE_H), 1};
           if (make_map4(mp, d->src[s] + ((int64_t)py * d->W + px) * cs, dims, str, box, "input(parity)")) return 1;
           have0 = true;
         }
@@ -847,13 +888,13 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   if (cg == 1) {
     int grid = vt_num_sms();
     if (grid > a.total_tiles) grid = a.total_tiles;
-    conv_tc_kernel<1><<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(a);
+    conv_tc_kernel<1><<<grid, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(a);
   } else {
     int pairs = vt_num_sms() / 2;
     if (pairs > a.total_tiles) pairs = a.total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];

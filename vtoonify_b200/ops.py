@@ -42,7 +42,7 @@ def get_precision() -> str:
 # (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 256, slower at Cin = 512:
 # tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
 import os as _os
-_options = {"fold_upconv": 256, "fuse_torgb": True, "fuse_mask_mul": True}
+_options = {"fold_upconv": 256, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 
@@ -440,12 +440,12 @@ def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], tap
                 bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, skip: Optional[torch.Tensor] = None,
                 skip_kernel: Optional[torch.Tensor] = None, mul_src: Optional[torch.Tensor] = None,
                 src2: Optional[torch.Tensor] = None, tap_const: Optional[torch.Tensor] = None,
-                src_mask: Optional[torch.Tensor] = None):
+                src_mask: Optional[torch.Tensor] = None, tsum: Optional[torch.Tensor] = None):
     """Cout<=4 convolution with planar NCHW output ``[B,Cout,H,W]``; optionally also returns ``mul_src * out[:,0]``.
     ``src2``: the input is the virtual concat ``[src | abs(src - src2)]`` (weight rows hold 2*C channels);
     ``tap_const`` ``[wB, w_taps, Cout]``: constant added for every in-bounds tap (folded AdaIN affine)."""
-    _req_cuda(src, weight, planar, planar_weight, bias, skip, skip_kernel, mul_src, src2, tap_const)
-    dev = (src if src is not None else planar).device
+    _req_cuda(src, weight, planar, planar_weight, bias, skip, skip_kernel, mul_src, src2, tap_const, tsum)
+    dev = next(t for t in (src, planar, tsum) if t is not None).device
     d = SmallNDesc()
     d.struct_size = _lib.ctypes.sizeof(SmallNDesc)
     if planar is not None:
@@ -471,7 +471,12 @@ def smalln_conv(src: Optional[torch.Tensor], weight: Optional[torch.Tensor], tap
                 raise _lib.VtError("smalln_conv: src_mask must be a contiguous [B,H,W] map")
             d.src_mask = src_mask.data_ptr()
     else:
-        d.wB, d.w_taps = 1, (planar_weight.shape[0] if planar_weight is not None else 1)
+        d.wB, d.w_taps = 1, (planar_weight.shape[0] if planar_weight is not None else len(taps))
+    if tsum is not None:
+        # NHWC [B,H,W,Ct] per-tap partial products from a 1x1 tensor-core convolution (rows t*Cout + n)
+        if tsum.shape[:3] != (B, H, W) or not tsum.is_contiguous() or tsum.shape[3] < len(taps) * Cout:
+            raise _lib.VtError("smalln_conv: bad tsum tensor")
+        d.tsum, d.tsum_c = tsum.data_ptr(), tsum.shape[3]
     d.Cout = Cout
     d.B, d.H, d.W = B, H, W
     d.taps = len(taps)

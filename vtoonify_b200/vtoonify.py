@@ -63,6 +63,19 @@ class Conv2d(nn.Module):
             self._w_planar = wt[:, :npl].permute(2, 3, 0, 1).reshape(k * k, wt.shape[0], npl).contiguous() if npl else None
             self._split_key = key
         w = self._wp.get(self._w_nhwc_part, 1.0, Cs, round_tf32=False)
+        n_out = self.weight.shape[0]
+        if (ops.scale_fusable() and ops.get_option("smalln_via_tc") and k == 3 and 9 * n_out <= 32 and Cs % 32 == 0
+                and act == ACT_NONE and mul_src is None):
+            # The 9*n_out per-tap dot products of every pixel are a [pixels x C] . [C x 32] GEMM: run it as a 1x1 convolution on
+            # the tensor cores (each input read once, at HBM speed), then sum the 9 shifted partial products per output pixel.
+            wkey = (w.data_ptr(), w._version)
+            if getattr(self, "_wT_key", None) != wkey:
+                wT = torch.zeros((1, 1, 32, w.shape[3]), device=w.device, dtype=torch.float32)
+                wT[0, 0, :9 * n_out] = w.reshape(9 * n_out, w.shape[3])
+                self._wT, self._wT_key = wT, wkey
+            T = ops.conv2d_nhwc([x], self._wT, [(0, 0, 0)], 1, H, W, src_scale=None if src_mask is None else [src_mask])
+            return ops.smalln_conv(None, None, ops.conv_taps(k, self.padding), n_out, B, H, W, planar=planar,
+                                   planar_weight=self._w_planar, bias=self.bias, tsum=T)
         return ops.smalln_conv(x, w, ops.conv_taps(k, self.padding), self.weight.shape[0], B, H, W, planar=planar,
                                planar_weight=self._w_planar, bias=self.bias, act=act, mul_src=mul_src, src_mask=src_mask)
 

@@ -1,0 +1,104 @@
+"""Full-size GPU checks of the BASELINE.json configurations. The CPU oracle needs ~20 s per 576x1024 frame, so at these
+sizes parity is established through (a) the fp32 FFMA mode of the same graph, which the golden tests pin to the reference
+at 1e-5, (b) a mid-size frame against the oracle itself, and (c) size-independent properties: batch independence of frames,
+determinism, finite outputs, output geometry."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+TOL = 1e-3      # per-pixel bar of BASELINE.json (north_star), relative to max(1, rms)
+
+
+def _model(backbone, seed=0):
+    from vtoonify_b200.vtoonify import VToonify
+    from vtoonify_b200.weights import det_state_dict
+    m = VToonify(backbone=backbone).eval()
+    sd = det_state_dict(m, seed=seed)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda(), sd
+
+
+def _cmp(y, ref, what, tol=TOL):
+    err = (y.double() - ref.double()).abs().max().item()
+    rms = ref.double().pow(2).mean().sqrt().item()
+    print(f"{what}: max|err| {err:.3e}, ref rms {rms:.3f}")
+    assert torch.isfinite(y).all()
+    assert err <= tol * max(1.0, rms), f"{what}: {err:.3e} > {tol} * max(1, {rms:.3f})"
+
+
+def test_vtoonify_d_midsize_vs_oracle():
+    """One 160x224 frame (tile-ragged at every level, all four fusion levels active) against the CPU oracle."""
+    from oracle import vt_oracle as O
+    from vtoonify_b200 import ops
+    from vtoonify_b200.weights import det_inputs
+    m, sd = _model("dualstylegan")
+    x, style = det_inputs(1, 160, 224, seed=5)
+    ref = O.vtoonify_forward(sd, x, style, 0.5, "dualstylegan")
+    assert ops.get_precision() == "bf16x3"
+    y = m(x.cuda(), style.cuda(), d_s=0.5)
+    assert tuple(y.shape) == (1, 3, 640, 896)
+    _cmp(y.cpu(), ref, "VToonify-D 160x224 [bf16x3] vs oracle")
+
+
+def test_vtoonify_d_bench_config_576x1024_b4():
+    """BASELINE configs[1] at full size: product mode vs the fp32 FFMA mode, batch independence, determinism."""
+    from vtoonify_b200 import ops
+    from vtoonify_b200.weights import det_inputs
+    m, _ = _model("dualstylegan")
+    x, style = det_inputs(4, 576, 1024, seed=0)
+    x, style = x.cuda(), style.cuda()
+    y = m(x, style, d_s=0.5)
+    assert tuple(y.shape) == (4, 3, 2304, 4096)
+    y_again = m(x, style, d_s=0.5)
+    assert torch.equal(y, y_again), "forward is not deterministic"
+    y1 = m(x[2:3], style[2:3], d_s=0.5)                      # frame 2 alone == frame 2 inside the batch
+    assert (y[2:3] - y1).abs().max().item() <= 1e-5
+    ops.set_precision("fp32")
+    try:
+        ref = m(x[:1], style[:1], d_s=0.5)
+    finally:
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    _cmp(y[:1].cpu(), ref.cpu(), "VToonify-D 576x1024 [bf16x3] vs fp32 mode")
+
+
+@pytest.mark.parametrize("hw", [(720, 1280), (712, 1272)])
+def test_vtoonify_t_variable_size_b2(hw):
+    """BASELINE configs[4]: Toonify backbone, 720x1280 (and a size that is not a multiple of 16) frames, batch 2."""
+    from vtoonify_b200 import ops
+    from vtoonify_b200.weights import det_inputs
+    m, _ = _model("toonify")
+    H, W = hw
+    x, style = det_inputs(2, H, W, seed=3)
+    x, style = x.cuda(), style.cuda()
+    y = m(x, style, d_s=0.5)
+    assert tuple(y.shape) == (2, 3, 4 * (H // 8 * 8), 4 * (W // 8 * 8)) or tuple(y.shape)[2:] == (4 * H, 4 * W), tuple(y.shape)
+    ops.set_precision("fp32")
+    try:
+        ref = m(x[1:], style[1:], d_s=0.5)
+    finally:
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    _cmp(y[1:].cpu(), ref.cpu(), f"VToonify-T {H}x{W} [bf16x3] vs fp32 mode")
+
+
+def test_generator_1024_b8():
+    """BASELINE configs[2]: 1024x1024 StyleGAN2 generator-only synthesis, batch 8."""
+    from vtoonify_b200 import ops
+    from vtoonify_b200.stylegan import Generator
+    from vtoonify_b200.weights import det_state_dict
+    g = Generator(1024, 512, 8).eval()
+    g.load_state_dict(det_state_dict(g, seed=3), strict=True)
+    g.cuda()
+    gen = torch.Generator().manual_seed(7)
+    latent = torch.randn((8, g.n_latent, 512), generator=gen).cuda()
+    img, _ = g([latent], input_is_latent=True, randomize_noise=False)
+    assert tuple(img.shape) == (8, 3, 1024, 1024) and torch.isfinite(img).all()
+    one, _ = g([latent[5:6]], input_is_latent=True, randomize_noise=False)
+    assert (img[5:6] - one).abs().max().item() <= 1e-5, "sample 5 differs between batch 8 and batch 1"
+    ops.set_precision("fp32")
+    try:
+        ref, _ = g([latent[:1]], input_is_latent=True, randomize_noise=False)
+    finally:
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    _cmp(img[:1].cpu(), ref.cpu(), "Generator(1024) [bf16x3] vs fp32 mode")

@@ -237,3 +237,28 @@ def test_upfirdn2d_tiled_and_generic_kernels_agree():
             assert y.shape == ref.shape, (H, W, kh, kw, up, down, pad)
             assert maxerr(y, ref) <= 2e-5 * max(1.0, ref.abs().max().item()), (H, W, kh, kw, up, down, pad, maxerr(y, ref))
         n += 1
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 33, 65), (1, 64, 17, 130), (1, 8, 9, 7)])
+def test_fir4_specialised_kernel_vs_generic_and_oracle(shape):
+    """4x4 pad (1,1) Blur on NHWC: register-tiled kernel vs the generic kernel vs upfirdn2d of the oracle (odd sizes = the
+    (2H+1)x(2W+1) output of a stride-2 transposed conv), with the fused noise + bias + leaky-relu tail."""
+    from vtoonify_b200 import _lib, ops
+    ops.set_precision("fp32")
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn((B, C, H, W), generator=g)
+    k = torch.randn((4, 4), generator=g)          # not separable on purpose: the kernel is used as given
+    bias = torch.randn(C, generator=g); noise = torch.randn((B, 1, H - 1, W - 1), generator=g); nw = torch.tensor([0.3])
+    ref = O.fused_leaky_relu(O.upfirdn2d(x, k, pad=(1, 1)) + nw * noise, bias)
+    lib = _lib.load()
+    outs = []
+    for mode in (0, 1):
+        old = lib.vt_set_option(b"fir4", mode)
+        try:
+            outs.append(ops.to_nchw(ops.fir_nhwc(ops.to_nhwc(x.cuda()), k.cuda(), (1, 1), bias=bias.cuda(), noise=noise.cuda(),
+                                                 noise_w=nw.cuda(), act=True)).cpu())
+        finally:
+            lib.vt_set_option(b"fir4", old)
+    ops.set_precision(ops.DEFAULT_PRECISION)
+    assert maxerr(outs[0], ref) <= 1e-5 and maxerr(outs[1], ref) <= 1e-5, (maxerr(outs[0], ref), maxerr(outs[1], ref))

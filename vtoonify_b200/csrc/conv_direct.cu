@@ -639,8 +639,8 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
   VT_CHECK(d->src_c == 0 || d->w_cstride >= cw, "smalln_conv: weight row shorter than the (virtual-concat) channel count");
   cudaStream_t st = (cudaStream_t)stream;
   // input-stationary kernel for 9-tap convolutions whose taps stay within +-2 pixels
-  // (measured on B200: faster than the gather kernel for Cout == 1 once there are >= 2 patches per SM, slower for Cout >= 2)
-  const bool is_auto = d->Cout == 1 && vt_cdiv(d->W, IS_PW) * vt_cdiv(d->H, IS_PH) * d->B >= 2 * (int64_t)vt_num_sms();
+  // (measured on B200: faster than the gather kernel for Cout == 1 on maps of >= 64 patches, slower for Cout >= 2)
+  const bool is_auto = d->Cout == 1 && vt_cdiv(d->W, IS_PW) * vt_cdiv(d->H, IS_PH) >= 64;   // per image: the choice must not depend on the batch size (frames are independent units)
   if ((g_smalln_is == 2 || (g_smalln_is == 1 && is_auto)) && d->taps == IS_TAPS && d->src_c >= 32) {
     int dy0 = 0, dy1 = 0, dx0 = 0, dx1 = 0;
     for (int t = 0; t < d->taps; ++t) {

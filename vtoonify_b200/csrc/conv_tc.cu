@@ -29,6 +29,7 @@ using namespace vt_tc;
 int vt_validate_conv_desc(const vt_conv_desc* d, const char* who);
 extern int g_upfirdn_tiled;
 extern int g_smalln_is;
+extern int g_fir4;
 
 namespace {
 
@@ -636,6 +637,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
   if (key && strcmp(key, "tc_transpose") == 0) { int old = g_tc_transpose; g_tc_transpose = value; return old; }
   if (key && strcmp(key, "tc_pair_y") == 0) { int old = g_tc_pair_y; g_tc_pair_y = value; return old; }
+  if (key && strcmp(key, "fir4") == 0) { int old = g_fir4; g_fir4 = value; return old; }
   if (key && strcmp(key, "smalln_is") == 0) { int old = g_smalln_is; g_smalln_is = value; return old; }
   if (key && strcmp(key, "upfirdn_tiled") == 0) { int old = g_upfirdn_tiled; g_upfirdn_tiled = value; return old; }
   return -1;

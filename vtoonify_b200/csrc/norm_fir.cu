@@ -10,6 +10,8 @@
 //        of a 1 x 4 vertical strip of outputs so every input row is loaded once per strip.
 #include "common.cuh"
 
+int g_fir4 = 1;   // 1: specialised 4x4 pad (1,1) FIR kernel; 0: generic kernel (tests / A-B)
+
 namespace {
 
 // Deterministic two-stage reduction (no atomics): stage 1 — grid (chunks, B): every thread owns one float4 channel
@@ -183,6 +185,99 @@ fir_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ kernel, 
   }
 }
 
+// 4x4 FIR, pad (1,1) (the Blur after a stride-2 transposed conv, model/stylegan/model.py:284-285): a thread owns 2 adjacent
+// output columns x FIR4_R rows of one 4-channel group.  Per input row it issues 5 independent 16-byte loads (clamped address +
+// zero mask, no branches), so 3.4 loads per output instead of 7 and all of them in flight together.
+constexpr int FIR4_R = 8;
+
+__global__ void __launch_bounds__(256)
+fir4_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ kernel, float* __restrict__ out, int H, int W,
+                 int C, int Ho, int Wo, const float* __restrict__ bias, const float* __restrict__ noise,
+                 const float* __restrict__ noise_w, int act, float slope, float gain, int round_tf32) {
+  __shared__ float sk[16];  // flipped kernel: sk[ky][kx] multiplies in[oy+ky-1][ox+kx-1]
+  if (threadIdx.x < 16) sk[threadIdx.x] = kernel[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)];
+  __syncthreads();
+  float kk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kk[i] = sk[i];
+  const int nvec = C / 4;
+  const int b = blockIdx.z;
+  const int strips = (Ho + FIR4_R - 1) / FIR4_R, pairs = (Wo + 1) / 2;
+  const int64_t total = (int64_t)strips * pairs * nvec;
+  const float nw = noise ? *noise_w : 0.f;
+  const float* ip = in + (int64_t)b * H * W * C;
+  float* op = out + (int64_t)b * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int64_t r = i / nvec;
+    const int ox0 = (int)(r % pairs) * 2;
+    const int oy0 = (int)(r / pairs) * FIR4_R;
+    float4 acc[FIR4_R][2];
+#pragma unroll
+    for (int j = 0; j < FIR4_R; ++j) acc[j][0] = acc[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx[5];
+    float mx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int ix = ox0 - 1 + k;
+      mx[k] = (ix >= 0 && ix < W) ? 1.f : 0.f;
+      cx[k] = ix < 0 ? 0 : (ix >= W ? W - 1 : ix);
+    }
+#pragma unroll
+    for (int ry = 0; ry < FIR4_R + 3; ++ry) {
+      const int iy = oy0 - 1 + ry;
+      const float my = (iy >= 0 && iy < H) ? 1.f : 0.f;
+      const int cy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);
+      const float* rowp = ip + (int64_t)cy * W * C + v * 4;
+      float4 a[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        a[k] = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)cx[k] * C));
+        const float m = my * mx[k];
+        a[k].x *= m; a[k].y *= m; a[k].z *= m; a[k].w *= m;
+      }
+#pragma unroll
+      for (int j = 0; j < FIR4_R; ++j) {
+        const int ky = ry - j;
+        if (ky >= 0 && ky < 4) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              const float w = kk[ky * 4 + kx];
+              acc[j][o].x = fmaf(a[o + kx].x, w, acc[j][o].x); acc[j][o].y = fmaf(a[o + kx].y, w, acc[j][o].y);
+              acc[j][o].z = fmaf(a[o + kx].z, w, acc[j][o].z); acc[j][o].w = fmaf(a[o + kx].w, w, acc[j][o].w);
+            }
+        }
+      }
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = *reinterpret_cast<const float4*>(bias + v * 4);
+    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int j = 0; j < FIR4_R; ++j) {
+      const int oy = oy0 + j;
+      if (oy >= Ho) break;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const int ox = ox0 + o;
+        if (ox >= Wo) continue;
+        float t4[4] = {acc[j][o].x, acc[j][o].y, acc[j][o].z, acc[j][o].w};
+        const float nz = noise ? nw * noise[((int64_t)b * Ho + oy) * Wo + ox] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t = t4[k];
+          if (noise) t += nz;
+          if (act) t = vt_lrelu(t + bb[k], slope) * gain;
+          else if (bias) t += bb[k];
+          t4[k] = round_tf32 ? vt_round_tf32(t) : t;
+        }
+        *reinterpret_cast<float4*>(op + ((int64_t)oy * Wo + ox) * C + v * 4) = make_float4(t4[0], t4[1], t4[2], t4[3]);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 static void instnorm_plan(int64_t HW, int C, int64_t* chunk, int64_t* chunks) {
@@ -247,6 +342,16 @@ extern "C" int vt_fir_nhwc_f32(const float* in, const float* kernel, float* out,
   VT_CHECK(!noise || noise_w, "fir_nhwc: noise without noise_w");
   const int Ho = H + pad0 + pad1 - kh + 1, Wo = W + pad0 + pad1 - kw + 1;
   VT_CHECK(Ho >= 1 && Wo >= 1, "fir_nhwc: empty output");
+  if (kh == 4 && kw == 4 && pad0 == 1 && pad1 == 1 && g_fir4) {
+    const int64_t total4 = (int64_t)vt_cdiv(Ho, FIR4_R) * vt_cdiv(Wo, 2) * (C / 4);
+    int64_t blocks4 = vt_cdiv(total4, 256);
+    const int64_t cap4 = (int64_t)vt_num_sms() * 16;
+    if (blocks4 > cap4) blocks4 = cap4;
+    fir4_nhwc_kernel<<<dim3((unsigned)blocks4, 1, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        in, kernel, out, H, W, C, Ho, Wo, bias, noise, noise_w, act, slope, gain, round_tf32);
+    VT_LAUNCH_CHECK();
+    return 0;
+  }
   const int strips = (Ho + FIR_R - 1) / FIR_R;
   const int64_t total = (int64_t)strips * Wo * (C / 4);
   int64_t blocks = vt_cdiv(total, 256);

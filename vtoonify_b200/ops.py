@@ -39,10 +39,10 @@ def get_precision() -> str:
 
 # algorithm switches (kept so tests can compare both formulations on the GPU)
 # fold_upconv: True = always fold Blur o conv_transpose into one N = 4*Cout convolution; an int = only when Cin <= that value
-# (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 256, slower at Cin = 512:
+# (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 128, slower from Cin = 256 up:
 # tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
 import os as _os
-_options = {"fold_upconv": 256, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True}
+_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 

@@ -88,8 +88,10 @@ int vt_fold_upconv_weights_f32(const float* w, const float* blur, float* out, in
                                void* stream);
 
 /* Split fp32 weight rows for the bf16x3 tensor-core mode: for every 32-channel chunk (128 bytes) of every row,
- * out = [bf16(w) x 32 | bf16(w - bf16(w)) x 32] (128 bytes). w, out: [rows][C] fp32-sized elements, C % 32 == 0. */
-int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, void* stream);
+ * out = [bf16(w) x 32 | bf16(w - bf16(w)) x 32] (128 bytes). w, out: [rows][C] fp32-sized elements, C % 32 == 0.
+ * nstack_rows > 0 (N-stacked form, rows % nstack_rows == 0): out has 2*rows rows; each group of nstack_rows input rows
+ * becomes nstack_rows rows [hi|hi] followed by nstack_rows rows [lo|lo]. */
+int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, int nstack_rows, void* stream);
 
 /* ---- convolution descriptor (NHWC activations) -------------------------------------------- */
 #define VT_MAX_TAPS 36     /* 9 taps x up to 4 output phases (folded up-conv) */
@@ -145,6 +147,9 @@ typedef struct vt_conv_desc {
   const void*  weight_bf16x3;   /* optional: `weight` split by vt_split_weights_bf16x3 (same shape/strides in bytes). When set, the
                                  * tensor-core kernel computes a*w as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with bf16 operands
                                  * (fp32-class accuracy, 1.5x the MMA work of TF32); ignored by the direct kernel          */
+  int32_t bf16x3_nstack;        /* 1: weight_bf16x3 is the N-stacked form of vt_split_weights_bf16x3 (Cout == 32 only): per tap 32 rows
+                                 * [w_hi|w_hi] then 32 rows [w_lo|w_lo]; 4 MMAs per tap instead of 6, all four hi/lo products        */
+  int32_t reserved2;
   const float* src_scale[2];    /* optional planar [B,H,W] per-pixel multiplier of source i, applied while the operand is split
                                  * (bf16x3 tensor-core mode, stride 1 only): conv(cat[f_G, f_E * m_E]) without materialising
                                  * f_E * m_E (model/vtoonify.py:127). Rejected by the other kernels.                        */

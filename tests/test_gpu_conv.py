@@ -500,3 +500,33 @@ def test_smalln_conv_via_tensor_core_tap_products(with_planar, with_mask):
         ops.set_precision(ops.DEFAULT_PRECISION)
     assert maxerr(y_g.cpu(), ref) <= 2e-5
     assert maxerr(y_tc.cpu(), ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("nstack", [False, True])
+@pytest.mark.parametrize("mt,cg2", [(0, 1), (1, 0), (2, 1), (4, 0)])
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[9], (2, 32, 32, 33, 70, 3, 1, 1, 1), (1, 128, 32, 24, 40, 3, 1, 2, 2)])
+def test_bf16x3_n_stacked_weights(case, mt, cg2, nstack):
+    """Cout == 32: weight rows stacked as [w_hi|w_hi] x32 + [w_lo|w_lo] x32 (N = 64, 4 MMAs per tap, halves summed in the
+    epilogue) vs the 6-instruction form vs the FFMA kernel; with noise / bias / residual."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007 + 31)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn((B, Cout, H, W), generator=g)
+    noise = torch.randn((B, 1, H, W), generator=g); nw = torch.tensor([0.3])
+    kw = dict(act=_lib.ACT_LRELU, slope=0.2, gain=1.25, alpha=0.5, beta=0.75, noise=noise.cuda(), noise_w=nw.cuda())
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    lib = _lib.load()
+    old = (lib.vt_set_option(b"tc_mt", mt), lib.vt_set_option(b"tc_cg2", cg2))
+    ops.set_option("bf16x3_nstack", nstack)
+    try:
+        y = _run(ops, x, w, b, k, stride, pad, dil, "bf16x3", res=ops.to_nhwc(res.cuda(), round_tf32=False), **kw)
+    finally:
+        ops.set_option("bf16x3_nstack", False)
+        lib.vt_set_option(b"tc_mt", old[0]); lib.vt_set_option(b"tc_cg2", old[1])
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    scale = max(1.0, ref.abs().max().item())
+    assert maxerr(y, ref) <= BF16X3_TOL * scale, f"nstack {nstack} mt {mt} cg2 {cg2}: {maxerr(y, ref):.3e} (scale {scale:.1f})"

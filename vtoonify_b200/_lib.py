@@ -34,7 +34,7 @@ class ConvDesc(Structure):
         ("round_tf32", c_int32), ("reserved", c_int32),
         ("rgb_w", c_void_p), ("rgb_bias", c_void_p), ("rgb_skip", c_void_p), ("rgb_skip_kernel", c_void_p),
         ("rgb_out", c_void_p),
-        ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("src_scale", c_void_p * 2),
+        ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("bf16x3_nstack", c_int32), ("reserved2", c_int32), ("src_scale", c_void_p * 2),
     ]
 
 
@@ -71,7 +71,7 @@ SYMBOLS = {
     "vt_pixelnorm_f32": (c_int, [_P, _P, c_int, c_int, _P]),
     "vt_modulate_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
     "vt_fold_upconv_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
-    "vt_split_weights_bf16x3": (c_int, [_P, _P, c_int64, c_int, _P]),
+    "vt_split_weights_bf16x3": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
     "vt_conv2d_direct_f32": (c_int, [POINTER(ConvDesc), _P]),
     "vt_conv2d_tc_tf32": (c_int, [POINTER(ConvDesc), _P]),
     "vt_conv2d_tc_supported": (c_int, [POINTER(ConvDesc)]),

@@ -74,6 +74,8 @@ struct TcArgs {
   const float* src_scale[2]; // bf16x3: optional planar per-pixel multiplier of source s (kernel-space strides below)
   int64_t sc_sb, sc_sy, sc_sx;
   int in_w, in_h;            // kernel-space input extents
+  int mma_n;                 // N of one MMA / TMEM columns per accumulator: block_n, or 2*block_n in the N-stacked bf16x3 form
+  int nstack;                // bf16x3, Cout == 32: weight rows [w_hi|w_hi] x32 then [w_lo|w_lo] x32 -> 4 MMAs per tap, halves summed in the epilogue
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
   int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
 };
@@ -200,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 if (CG == 2) {   // this CTA stages rows [rank*block_n/2, +block_n/2) of the weight tile
                   if (rank == 0) mbar_arrive_expect_tx(b_full(b_st), 2u * (uint32_t)p.b_tx_bytes);
                   tma_load_4d_2sm(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), wc,
-                                  n0 + (int)rank * (p.block_n / 2), p.step_w[j], wb);
+                                  (p.nstack ? 0 : n0) + (int)rank * (p.mma_n / 2), p.step_w[j], wb);
                 } else {
                   mbar_arrive_expect_tx(b_full(b_st), (uint32_t)p.b_tx_bytes);
                   tma_load_4d(b_base + b_st * p.b_stage_bytes, &p.w_map, b_full(b_st), wc, n0, p.step_w[j], wb);
@@ -216,14 +218,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     }
   } else if (warp == 1 && rank == 0) {
     // ================= MMA issuer (whole warp converged; one elected lane issues; CTA rank 0 only) =================
-    const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(TILE_M * CG, p.block_n) : make_idesc_tf32(TILE_M * CG, p.block_n);
+    const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(TILE_M * CG, p.mma_n) : make_idesc_tf32(TILE_M * CG, p.mma_n);
     int a_st = 0, b_st = 0, as = 0;
     uint32_t a_par = 0, b_par = 0, t_par = 0;
-    const uint32_t tile_bytes_n = (uint32_t)(p.block_n / CG) * 128u;   // bytes of one tap's weight rows held by this CTA
+    const uint32_t tile_bytes_n = (uint32_t)(p.mma_n / CG) * 128u;   // bytes of one tap's weight rows held by this CTA
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
       VT_TWAIT(2, mbar_wait(t_empty(as), t_par ^ 1, 4));
       tc_fence_after();
-      const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * p.mt * p.block_n);
+      const uint32_t d_tmem0 = tmem_base + (uint32_t)(as * p.mt * p.mma_n);
       uint32_t first = 1;   // first K step of this work item overwrites the accumulators
       for (int s = 0; s < p.n_src; ++s) {
         for (int kc = 0; kc < p.kchunks[s]; ++kc) {
@@ -253,8 +255,22 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             if (elect_one()) {
               for (int g = 0; g < p.mt; ++g) {
                 const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)(g * TILE_W * 128), sbo, 0);
-                const uint32_t d_tmem = d_tmem0 + (uint32_t)(g * p.block_n);
-                if (p.bf16x3) {
+                const uint32_t d_tmem = d_tmem0 + (uint32_t)(g * p.mma_n);
+                if (p.nstack) {
+                  // [a_hi|a_lo] (K = 64) x rows [w_hi|w_hi] (columns 0..31) and [w_lo|w_lo] (columns 32..63): all four products,
+                  // 4 instructions per tap instead of 6; the epilogue adds the two column halves
+                  if (CG == 2) {
+                    umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                    umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                    umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                    umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                  } else {
+                    umma_bf16(d_tmem, adesc, bdesc, idesc, first ^ 1u);
+                    umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                    umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                    umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                  }
+                } else if (p.bf16x3) {
                   // a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the dropped a_lo*w_lo term is ~2^-18 relative). The A row is
                   // [a_hi(32)|a_lo(32)] and the B row [w_hi(32)|w_lo(32)] bf16; +2 on a descriptor = +32 B = 16 bf16 of K.
                   if (CG == 2) {
@@ -382,6 +398,17 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
       const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
+      // single-phase layers: fetch this thread's noise values before waiting for the accumulators (an exposed HBM latency per
+      // tile otherwise; the noise map is streamed once)
+      float nz_pre[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.noise && p.n_phase == 1) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int oy = oy0 + ty, ox = ox0 + g * TILE_W + tx;
+          if (g < p.mt && oy < p.Ho && ox < p.Wo)
+            nz_pre[g] = nw * __ldg(p.noise + p.phase_pix[0] + (int64_t)b * p.pix_sb + (int64_t)oy * p.pix_sy + (int64_t)ox * p.pix_sx);
+        }
+      }
       VT_TWAIT(0, mbar_wait(t_full(as), t_par, 8));
       tc_fence_after();
       const int ph0 = n0 / p.Cout, nb0 = n0 - ph0 * p.Cout;   // once per work item
@@ -397,9 +424,15 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           nb += 32;
           if (nb >= p.Cout) { nb -= p.Cout; ++ph; }
           const int64_t off = p.phase_off[ph] + off0;
-          const float nz = (p.noise && in_img) ? nw * p.noise[p.phase_pix[ph] + pix0] : 0.f;
+          const float nz = p.n_phase == 1 ? nz_pre[g] : ((p.noise && in_img) ? nw * p.noise[p.phase_pix[ph] + pix0] : 0.f);
           float v[32];
-          VT_TWAIT(1, tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.block_n + j * 32), v));
+          VT_TWAIT(1, tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.mma_n + j * 32), v));
+          if (p.nstack) {   // second column half: the w_lo products
+            float v2[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.mma_n + 32), v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
           const long long t_math0 = p.dbg ? clock64() : 0;
           if (g == p.mt - 1 && j == nchunks - 1) {
             // every accumulator of this stage is in registers: hand the TMEM stage back to the MMA warp
@@ -617,6 +650,7 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
   VT_SUP((!d->src_scale[0] && !d->src_scale[1]) || (d->weight_bf16x3 && d->stride == 1), "conv_tc: src_scale needs the bf16x3 mode and stride 1");
+  VT_SUP(!d->bf16x3_nstack || (d->weight_bf16x3 && d->Cout == 32 && d->n_phase == 1), "conv_tc: the N-stacked bf16x3 form needs Cout == 32 and one phase");
   VT_SUP(!d->weight_bf16x3 || d->w_cstride % KCH == 0, "conv_tc: bf16x3 weights need a channel stride that is a multiple of 32");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
   VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
@@ -688,6 +722,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;
   a.bf16x3 = d->weight_bf16x3 != nullptr;
+  a.nstack = (a.bf16x3 && d->bf16x3_nstack) ? 1 : 0;
   a.src_scale[0] = d->src_scale[0]; a.src_scale[1] = d->src_scale[1];
   a.in_w = gW; a.in_h = gH;
   a.sc_sb = (int64_t)d->H * d->W; a.sc_sy = T ? 1 : d->W; a.sc_sx = T ? d->W : 1;
@@ -720,6 +755,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   int bn = 256;
   while (bn > 32 && (n_eff % bn) != 0) bn -= 32;
   VT_CHECK(n_eff % bn == 0, "conv_tc: no N tile for N=%d", n_eff);
+  const int bnm = a.nstack ? 2 * bn : bn;   // MMA N = TMEM columns per accumulator = weight rows per tile
   // halo staging: multi-tap layers (one box serves all taps) and small-N 1x1 layers (several M tiles per box and weight tile).
   // tc_mode 3: halo for stride 1 only (A/B tests)
   const bool can_halo = (g_tc_mode != 0) && (d->taps > 1 || (bn <= 64 && d->stride == 1)) && (d->stride == 1 || g_tc_mode != 3);
@@ -729,8 +765,8 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   if (can_halo && g_tc_mt != 1) {
     int want = (g_tc_mt > 0) ? g_tc_mt : (bn >= 256 ? 1 : (bn >= 128 ? 2 : 4));
     // keep two accumulator stages (epilogue/mainloop overlap) unless forced: 2 * n_phase * mt * bn <= 512 TMEM columns
-    const int col_budget = (g_tc_mt > 0) ? 512 : ((2 * bn <= 512) ? 256 : 512);
-    while (want > 1 && (want * bn > col_budget || gWo <= TILE_W * (want / 2))) want /= 2;
+    const int col_budget = (g_tc_mt > 0) ? 512 : ((2 * bnm <= 512) ? 256 : 512);
+    while (want > 1 && (want * bnm > col_budget || gWo <= TILE_W * (want / 2))) want /= 2;
     mt = want;
   }
   const int fixed = 2 * STAGING_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
@@ -739,7 +775,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   int tgroup = 1;
   if (g_tc_tgroup != 1) {
     for (int tg = d->taps; tg >= 2; --tg) {
-      if (d->taps % tg != 0 || tg * bn * 128 > (g_tc_tgroup > 1 ? g_tc_tgroup : 36) * 1024) continue;
+      if (d->taps % tg != 0 || tg * bnm * 128 > (g_tc_tgroup > 1 ? g_tc_tgroup : 36) * 1024) continue;
       bool ok = true;
       for (int t = 0; t < d->taps && ok; ++t)
         if (t % tg != 0 && d->tap_w[t] != d->tap_w[t - 1] + 1) ok = false;
@@ -782,7 +818,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
       halo_bytes = (int)(vt_cdiv(halo_bytes + w * h * 128, 1024) * 1024);
     }
     a.halo = can_halo && fits && halo_bytes <= 96 * 1024 && (mt > 1 || tx_bytes <= d->taps * TILE_M * 128 / 2) &&
-             2 * halo_bytes + 2 * (bn / cg) * 128 * tgroup + fixed <= MAX_SMEM;   // at least a 2+2 stage pipeline must fit
+             2 * halo_bytes + 2 * (bnm / cg) * 128 * tgroup + fixed <= MAX_SMEM;   // at least a 2+2 stage pipeline must fit
     if (!a.halo && mt > 1) continue;
     if (!a.halo) cg = 1;
     a.halo_x0 = a.hv_x0[0]; a.halo_y0 = a.hv_y0[0]; a.halo_w = hv_w[a.hv_view[0]];
@@ -790,7 +826,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     a.a_rows = a.halo ? (a.hv_off[a.n_hv - 1] + a.hv_bytes[a.n_hv - 1]) / 128 : TILE_M;
     // shared memory plan: A ring (halo boxes or per-tap tiles) + B ring (weight tiles) + 2 output staging buffers
     a.a_stage_bytes = a.halo ? halo_bytes : TILE_M * 128;
-    a.b_stage_bytes = (bn / cg) * 128 * tgroup;
+    a.b_stage_bytes = (bnm / cg) * 128 * tgroup;
     a.a_stages = a.halo ? 3 : 4;
     a.b_stages = tgroup > 1 ? 4 : (cg == 2 ? 8 : 6);
     while (a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed > MAX_SMEM) {
@@ -802,7 +838,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed;
     if (smem_bytes <= MAX_SMEM || mt == 1) break;
   }
-  a.b_tx_bytes = (bn / cg) * 128 * tgroup;
+  a.b_tx_bytes = (bnm / cg) * 128 * tgroup;
   VT_CHECK(smem_bytes <= MAX_SMEM && a.a_stages >= 2 && a.b_stages >= 2 && a.a_stages <= 8 && a.b_stages <= 8,
            "conv_tc: shared memory plan does not fit (%d B, mt=%d, bn=%d)", smem_bytes, mt, bn);
   for (int t = 0; t < d->taps; ++t) {
@@ -813,11 +849,12 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     a.step_sbo[t] = (uint16_t)(hv_w[v] * 128);
   }
   a.mt = mt;
-  a.acc_stages = (2 * mt * bn <= 512) ? 2 : 1;
+  a.acc_stages = (2 * mt * bnm <= 512) ? 2 : 1;
   int tc = 32;
-  while (tc < a.acc_stages * mt * bn) tc *= 2;
+  while (tc < a.acc_stages * mt * bnm) tc *= 2;
   a.tmem_cols = tc;
   a.block_n = bn;
+  a.mma_n = bnm;
   a.n_tiles = n_eff / bn;
   // pair orientation: side by side (x) or stacked (y), whichever wastes fewer tiles; ties -> x
   if (cg == 2) {
@@ -863,9 +900,11 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     const uint64_t str[3] = {wc * 4, (uint64_t)n_eff * wc * 4, (uint64_t)d->w_taps * n_eff * wc * 4};
     if (a.bf16x3) {   // same byte layout as the fp32 tensor: every 32-channel chunk is [w_hi(32) | w_lo(32)] bf16
       VT_CHECK(((uintptr_t)d->weight_bf16x3 & 15) == 0, "conv_tc: weight_bf16x3 not 16-byte aligned");
-      const uint64_t dims2[4] = {2 * wc, (uint64_t)n_eff, (uint64_t)d->w_taps, (uint64_t)d->wB};
-      const uint32_t box[4] = {2 * KCH, (uint32_t)(bn / cg), (uint32_t)a.tgroup, 1};
-      if (make_map4(&a.w_map, d->weight_bf16x3, dims2, str, box, "weight(bf16x3)", true)) return 1;
+      const uint64_t rows = (uint64_t)n_eff * (a.nstack ? 2 : 1);   // N-stacked: 32 [w_hi|w_hi] rows then 32 [w_lo|w_lo] rows per tap
+      const uint64_t dims2[4] = {2 * wc, rows, (uint64_t)d->w_taps, (uint64_t)d->wB};
+      const uint64_t str2[3] = {wc * 4, rows * wc * 4, (uint64_t)d->w_taps * rows * wc * 4};
+      const uint32_t box[4] = {2 * KCH, (uint32_t)(bnm / cg), (uint32_t)a.tgroup, 1};
+      if (make_map4(&a.w_map, d->weight_bf16x3, dims2, str2, box, "weight(bf16x3)", true)) return 1;
     } else {
       const uint32_t box[4] = {KCH, (uint32_t)(bn / cg), (uint32_t)a.tgroup, 1};
       if (make_map4(&a.w_map, d->weight, dims, str, box, "weight")) return 1;

@@ -189,9 +189,11 @@ extern "C" int vt_modulate_weights_f32(const float* W, const float* style, float
 }
 
 // ---- bf16x3 weight split -----------------------------------------------------------------------------------------
-// one thread per (row, 32-channel chunk, 4-channel group): reads a float4, writes 2 bf16x4 halves
+// one thread per (row, 32-channel chunk, 4-channel group): reads a float4, writes 2 bf16x4 halves.
+// nstack_rows == 0: out row = in row, chunk = [hi(32) | lo(32)].  nstack_rows = R > 0: input rows are taken in groups of R;
+// group g becomes R rows [hi|hi] followed by R rows [lo|lo] (output row stride unchanged, twice as many rows).
 __global__ void __launch_bounds__(256)
-split_bf16x3_kernel(const float* __restrict__ w, uint2* __restrict__ out, int64_t n_quads) {
+split_bf16x3_kernel(const float* __restrict__ w, uint2* __restrict__ out, int64_t n_quads, int C, int nstack_rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_quads) return;
   const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
@@ -203,18 +205,32 @@ split_bf16x3_kernel(const float* __restrict__ w, uint2* __restrict__ out, int64_
     h[k] = __bfloat16_as_ushort(hb);
     l[k] = __bfloat16_as_ushort(__float2bfloat16_rn(f[k] - __bfloat162float(hb)));
   }
+  const uint2 hq = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  const uint2 lq = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
   const int64_t chunk = i >> 3;          // 8 quads per 32-channel chunk
   const int q = (int)(i & 7);
-  uint2* base = out + chunk * 16;        // a chunk is 128 bytes = 16 uint2
-  base[q] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-  base[8 + q] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  if (nstack_rows == 0) {
+    uint2* base = out + chunk * 16;      // a chunk is 128 bytes = 16 uint2
+    base[q] = hq;
+    base[8 + q] = lq;
+  } else {
+    const int cpr = C / 32;              // chunks per row
+    const int64_t row = chunk / cpr;
+    const int cc = (int)(chunk - row * cpr);
+    const int64_t grp = row / nstack_rows, rr = row - grp * nstack_rows;
+    uint2* hi_row = out + (((grp * 2) * nstack_rows + rr) * cpr + cc) * 16;
+    uint2* lo_row = out + (((grp * 2 + 1) * nstack_rows + rr) * cpr + cc) * 16;
+    hi_row[q] = hq; hi_row[8 + q] = hq;
+    lo_row[q] = lq; lo_row[8 + q] = lq;
+  }
 }
 
-extern "C" int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, void* stream) {
+extern "C" int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, int nstack_rows, void* stream) {
   VT_CHECK(w && out && rows >= 1 && C >= 32 && C % 32 == 0, "split_weights_bf16x3: bad args (rows=%lld C=%d)", (long long)rows, C);
+  VT_CHECK(nstack_rows >= 0 && (nstack_rows == 0 || rows % nstack_rows == 0), "split_weights_bf16x3: rows must be a multiple of nstack_rows");
   VT_CHECK(((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 15) == 0, "split_weights_bf16x3: pointers must be 16-byte aligned");
   const int64_t n_quads = rows * C / 4;
-  split_bf16x3_kernel<<<(unsigned)vt_cdiv(n_quads, 256), 256, 0, (cudaStream_t)stream>>>(w, (uint2*)out, n_quads);
+  split_bf16x3_kernel<<<(unsigned)vt_cdiv(n_quads, 256), 256, 0, (cudaStream_t)stream>>>(w, (uint2*)out, n_quads, C, nstack_rows);
   VT_LAUNCH_CHECK();
   return 0;
 }

@@ -42,7 +42,7 @@ def get_precision() -> str:
 # (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 128, slower from Cin = 256 up:
 # tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
 import os as _os
-_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True}
+_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 
@@ -319,7 +319,12 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     use_tc = prec in ("tf32", "bf16x3") and lib.vt_conv2d_tc_supported(d)
     d.weight_bf16x3 = None
     if use_tc and prec == "bf16x3":
-        d.weight_bf16x3 = split_weights_bf16x3(weight).data_ptr()
+        # Cout == 32: the N-stacked form needs 4 instead of 6 MMA instructions per tap (and keeps all four hi/lo products);
+        # measured on B200 it is no faster (N = 64 MMAs take ~1.5x the time of N = 32 ones: these layers are bound by the
+        # shared-memory operand reads of the MMAs, not by instruction issue), so it is off by default
+        nstack = bool(_options["bf16x3_nstack"]) and Cout == 32 and phase_offs is None
+        d.weight_bf16x3 = split_weights_bf16x3(weight, nstack).data_ptr()
+        d.bf16x3_nstack = 1 if nstack else 0
     if use_tc:
         if _tc_profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,20 +342,22 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     return out if rgb is None else (out, rgb_out)
 
 
-def split_weights_bf16x3(weight: torch.Tensor) -> torch.Tensor:
+def split_weights_bf16x3(weight: torch.Tensor, nstack: bool = False) -> torch.Tensor:
     """``weight`` (from :func:`prep_weights` / :func:`fold_upconv_weights`, unrounded fp32, channel stride % 32 == 0) ->
-    same-shape buffer whose 32-channel chunks hold ``[bf16(w) | bf16(w - bf16(w))]``. Cached on the tensor object, so cached
-    plain-conv weights are split once; per-frame modulated weights are split per call (one tiny launch)."""
+    buffer whose 32-channel chunks hold ``[bf16(w) | bf16(w - bf16(w))]``; ``nstack`` (Cout == 32): per tap 32 rows ``[hi|hi]``
+    then 32 rows ``[lo|lo]`` (twice the rows). Cached on the tensor object, so cached plain-conv weights are split once;
+    per-frame modulated weights are split per call (one tiny launch)."""
     ver = weight._version
     cached = getattr(weight, "_vt_bf16x3", None)
-    if cached is not None and cached[0] == ver and cached[1] == weight.data_ptr():
+    if cached is not None and cached[0] == ver and cached[1] == weight.data_ptr() and cached[3] == nstack:
         return cached[2]
     if weight.shape[-1] % 32 != 0 or not weight.is_contiguous():
         raise _lib.VtError("split_weights_bf16x3: weight channel stride must be a multiple of 32")
-    out = torch.empty_like(weight)
-    check(_lib.load().vt_split_weights_bf16x3(weight.data_ptr(), out.data_ptr(), weight.numel() // weight.shape[-1],
-                                             weight.shape[-1], _stream()))
-    weight._vt_bf16x3 = (ver, weight.data_ptr(), out)
+    rows = weight.numel() // weight.shape[-1]
+    nrows = weight.shape[-2] if nstack else 0
+    out = torch.empty((2 * rows if nstack else rows, weight.shape[-1]), device=weight.device, dtype=torch.float32)
+    check(_lib.load().vt_split_weights_bf16x3(weight.data_ptr(), out.data_ptr(), rows, weight.shape[-1], nrows, _stream()))
+    weight._vt_bf16x3 = (ver, weight.data_ptr(), out, nstack)
     return out
 
 

@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
                        "backbone": "dualstylegan", "batch_per_step": 1},
             "cpu_baseline": cb,
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -284,7 +284,19 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if cb:
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Write the result line to the process's original stdout (fd 1 is pointed at stderr while the benchmark runs so that
+    library chatter such as NCCL's version banner cannot end up next to the JSON line)."""
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
 
 
 def main():
@@ -303,6 +315,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

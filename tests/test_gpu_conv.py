@@ -530,3 +530,41 @@ def test_bf16x3_n_stacked_weights(case, mt, cg2, nstack):
         ops.set_precision(ops.DEFAULT_PRECISION)
     scale = max(1.0, ref.abs().max().item())
     assert maxerr(y, ref) <= BF16X3_TOL * scale, f"nstack {nstack} mt {mt} cg2 {cg2}: {maxerr(y, ref):.3e} (scale {scale:.1f})"
+
+
+@pytest.mark.parametrize("transpose", [0, 2])
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[7], (2, 32, 32, 33, 70, 3, 1, 1, 1), "up"])
+def test_tc_epilogue_direct_global_stores(case, transpose):
+    """Epilogue variant that writes each pixel's 128-byte channel run straight to global memory (no smem staging / TMA store):
+    partial tiles, strided phase views (folded up-conv), transposed view, residual + noise."""
+    from vtoonify_b200 import _lib, ops
+    from oracle import vt_oracle as O
+    lib = _lib.load()
+    old = (lib.vt_set_option(b"tc_direct_store", 1), lib.vt_set_option(b"tc_transpose", transpose))
+    ops.set_precision("bf16x3")
+    try:
+        g = torch.Generator().manual_seed(41)
+        if case == "up":
+            B, Cin, Cout, H, W = 2, 64, 32, 7, 9
+            x = torch.randn((B, Cin, H, W), generator=g)
+            w = torch.randn((Cout, Cin, 3, 3), generator=g) / np.sqrt(Cin * 9)
+            k4 = O.make_kernel([1, 3, 3, 1]) * 4
+            bias = torch.randn(Cout, generator=g); noise = torch.randn((B, 1, 2 * H, 2 * W), generator=g); nw = torch.tensor([0.2])
+            ref = O.upfirdn2d(F.conv_transpose2d(x, w.transpose(0, 1), stride=2), k4, pad=(1, 1))
+            ref = F.leaky_relu(ref + nw * noise + bias.view(1, -1, 1, 1), 0.2) * 1.4142135
+            wf = ops.fold_upconv_weights(ops.prep_weights(w.cuda(), cin_pad=Cin), k4.cuda())
+            y = ops.to_nchw(ops.conv_up2_folded_nhwc(ops.to_nhwc(x.cuda()), wf, bias=bias.cuda(), noise=noise.cuda(), noise_w=nw.cuda(),
+                                                     act=1, gain=1.4142135)).cpu()
+        else:
+            B, Cin, Cout, H, W, k, stride, pad, dil = case
+            x = torch.randn((B, Cin, H, W), generator=g)
+            w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+            b = torch.randn(Cout, generator=g)
+            Ho, Wo = ops.conv_out_size(H, k, stride, pad, dil), ops.conv_out_size(W, k, stride, pad, dil)
+            res = torch.randn((B, Cout, Ho, Wo), generator=g)
+            ref = F.conv2d(x, w, b, stride=stride, padding=pad, dilation=dil) * 0.5 + 0.75 * res
+            y = _run(ops, x, w, b, k, stride, pad, dil, "bf16x3", res=ops.to_nhwc(res.cuda()), alpha=0.5, beta=0.75)
+    finally:
+        lib.vt_set_option(b"tc_direct_store", old[0]); lib.vt_set_option(b"tc_transpose", old[1])
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    assert maxerr(y, ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item()), f"{maxerr(y, ref):.3e}"

@@ -111,7 +111,8 @@ def load():
         fn.argtypes = args
     if lib.vt_abi_version() != 1:
         raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects 1")
-    for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup"), ("VT_TC_CG2", b"tc_cg2")):
+    for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup"), ("VT_TC_CG2", b"tc_cg2"),
+                     ("VT_TC_DIRECT_STORE", b"tc_direct_store")):
         if os.environ.get(env) is not None and os.environ.get(env) != "":
             lib.vt_set_option(key, int(os.environ[env]))      # tuning experiments only
     _lib = lib

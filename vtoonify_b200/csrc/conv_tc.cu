@@ -63,6 +63,7 @@ struct TcArgs {
   const float* noise;
   const float* noise_w;
   const float* res;
+  float* out;                // output base (direct-store epilogue; the TMA path goes through out_map)
   int64_t out_sb, out_sy, out_sx, phase_off[4];
   int64_t pix_sb, pix_sy, pix_sx, phase_pix[4];   // the same view in dense-pixel units (noise index), = offsets / out_cpitch
   int act, round_tf32;
@@ -76,6 +77,7 @@ struct TcArgs {
   int in_w, in_h;            // kernel-space input extents
   int mma_n;                 // N of one MMA / TMEM columns per accumulator: block_n, or 2*block_n in the N-stacked bf16x3 form
   int nstack;                // bf16x3, Cout == 32: weight rows [w_hi|w_hi] x32 then [w_lo|w_lo] x32 -> 4 MMAs per tap, halves summed in the epilogue
+  int direct_store;          // epilogue writes its 128-byte pixel rows straight to global memory instead of smem staging + TMA store
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
   int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
 };
@@ -511,6 +513,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               rgb2 = fmaf(v[4 * i], a2.x, rgb2); rgb2 = fmaf(v[4 * i + 1], a2.y, rgb2); rgb2 = fmaf(v[4 * i + 2], a2.z, rgb2); rgb2 = fmaf(v[4 * i + 3], a2.w, rgb2);
             }
           }
+          if (p.direct_store) {
+            // each thread owns one pixel's 32-channel run = one full 128-byte line of the NHWC output: no staging, no barriers
+            if (in_img) {
+              float4* op = reinterpret_cast<float4*>(p.out + off + nb);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) op[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            }
+          } else {
           const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
           if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
           named_bar_sync(1, 128);
@@ -527,6 +537,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
           if (store_thread) {
             tma_store_4d(&p.out_map[ph], sbuf, nb, ox0 + g * TILE_W, oy0, b);
             tma_store_commit();
+          }
           }
           if (p.dbg) tw[3] += clock64() - t_st0;
         }
@@ -634,6 +645,7 @@ unsigned long long* g_tc_dbg = nullptr;   // device buffer [148][16] set through
 int g_tc_cg2 = 1;     // 1: use CTA pairs (cta_group::2, M = 256) for N-tile-256 stride-1 halo convolutions
 int g_tc_transpose = 1;   // 1: hand the problem over transposed when that wastes fewer tiles; 0: never; 2: always (tests)
 int g_tc_pair_y = -1;     // -1: automatic pair orientation; 0/1: forced (tests)
+int g_tc_direct_store = 0;  // epilogue output path: 0 = smem staging + TMA store, 1 = direct 128-byte row stores, 2 = direct for N <= 128
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
@@ -668,6 +680,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
+  if (key && strcmp(key, "tc_direct_store") == 0) { int old = g_tc_direct_store; g_tc_direct_store = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
   if (key && strcmp(key, "tc_transpose") == 0) { int old = g_tc_transpose; g_tc_transpose = value; return old; }
   if (key && strcmp(key, "tc_pair_y") == 0) { int old = g_tc_pair_y; g_tc_pair_y = value; return old; }
@@ -717,6 +730,8 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     }
   }
   a.dbg = g_tc_dbg;
+  a.out = d->out;
+  a.direct_store = (g_tc_direct_store == 1) || (g_tc_direct_store == 2 && d->n_phase * d->Cout <= 128);
   a.slope_vec = d->slope_vec;
   a.rgb_w = d->rgb_w; a.rgb_bias = d->rgb_bias; a.rgb_skip = d->rgb_skip; a.rgb_skip_kernel = d->rgb_skip_kernel; a.rgb_out = d->rgb_out;
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;

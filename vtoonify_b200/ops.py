@@ -315,7 +315,7 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 d.src_scale[i] = sc.data_ptr()
     lib = _lib.load()
     if prec == "bf16x3":
-        d.weight_bf16x3 = 1   # placeholder so that vt_conv2d_tc_supported sees the mode; replaced below
+        d.weight_bf16x3 = weight.data_ptr()   # marks the mode for vt_conv2d_tc_supported; the split buffer is attached below
     use_tc = prec in ("tf32", "bf16x3") and lib.vt_conv2d_tc_supported(d)
     d.weight_bf16x3 = None
     if use_tc and prec == "bf16x3":

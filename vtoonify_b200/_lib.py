@@ -10,6 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvtoonify_b200.so")
+ABI_VERSION = 2
 VT_MAX_TAPS = 36
 ACT_NONE, ACT_LRELU, ACT_RELU_TANH = 0, 1, 2
 
@@ -109,8 +110,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.vt_abi_version() != 1:
-        raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects 1")
+    if lib.vt_abi_version() != ABI_VERSION:
+        raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects {ABI_VERSION}")
     for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup"), ("VT_TC_CG2", b"tc_cg2"),
                      ("VT_TC_DIRECT_STORE", b"tc_direct_store")):
         if os.environ.get(env) is not None and os.environ.get(env) != "":

@@ -126,3 +126,29 @@ def test_psp_state_dict_contract():
     assert all(list(sd[k].shape) == keys[k] for k in keys)
     cfg = get_blocks(50)
     assert len(cfg) == 24 and [i for i, c in enumerate(cfg) if c[2] == 2] == [0, 3, 7, 21]
+
+
+def test_precision_and_algorithm_switches():
+    """Host-side configuration: the product precision is the split-bf16 mode (the one that meets the 1e-3 bar); the up-conv
+    formulation is chosen per layer by input channels; unknown names fail loudly."""
+    import pytest
+    from vtoonify_b200 import ops
+    assert ops.DEFAULT_PRECISION == "bf16x3" and ops.get_precision() == "bf16x3"
+    old = ops.set_precision("tf32")
+    try:
+        assert old == "bf16x3" and ops.get_precision() == "tf32"
+        assert ops.scale_fusable() is False            # f_E * m_E fusion needs the operand-transform warps of the bf16x3 mode
+    finally:
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    assert ops.scale_fusable() is True
+    with pytest.raises(ValueError):
+        ops.set_precision("fp16")
+    with pytest.raises(KeyError):
+        ops.set_option("no_such_option", 1)
+    thr = ops.get_option("fold_upconv")
+    assert ops.use_folded_upconv(64) and ops.use_folded_upconv(int(thr)) and not ops.use_folded_upconv(512)
+    ops.set_option("fold_upconv", True)
+    try:
+        assert ops.use_folded_upconv(512)
+    finally:
+        ops.set_option("fold_upconv", thr)

@@ -5,6 +5,7 @@ Internal activation layout is NHWC (``[B, H, W, C]`` contiguous fp32); the refer
 convert at the API boundary (NCHW in / out, or zero-copy when a tensor is channels_last).
 """
 import math
+import os as _os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -14,13 +15,13 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU_TANH, ConvDesc, SmallNDesc, chec
 
 SQRT2 = math.sqrt(2.0)
 
-# "bf16x3" (default, the product path): tcgen05 tensor-core convolutions that meet the 1e-3 per-pixel parity bar — the kernel
-#   below with
-# "tf32": tcgen05 tensor-core convolutions with TF32 operands (fp32 accumulate): ~20% faster end to end, but 10-bit mantissas
-#   put the 50-layer VToonify-D output 2.8-4e-3 away from the fp32 reference (measured), above the parity bar. Opt-in.
-# "bf16x3": the same tensor-core kernel with every fp32 operand split into bf16 hi + lo parts in shared memory and three
-#   MMA products per K step (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate): fp32-class accuracy at 1.5x the MMA work.
-# "fp32": every convolution on the fp32-exact FFMA kernel (used to cross-check the tensor-core path).
+# Convolution arithmetic (set_precision):
+# "bf16x3" (default, the product path): tcgen05 tensor-core convolutions with every fp32 operand split into bf16 hi + lo parts
+#   (pixels in shared memory, weights by vt_split_weights_bf16x3) and three MMA products per K step, fp32 accumulate:
+#   a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.  Meets the 1e-3 per-pixel parity bar (measured 3.4e-4 end to end).
+# "tf32": the same kernel with TF32 operands: ~7 % faster end to end, but 10-bit mantissas put the ~47-layer VToonify-D output
+#   3-4e-3 away from the fp32 reference (measured), above the parity bar.  Opt-in.
+# "fp32": every convolution on the fp32-exact FFMA kernel (used to cross-check the tensor-core paths).
 DEFAULT_PRECISION = "bf16x3"
 _precision = DEFAULT_PRECISION
 
@@ -41,7 +42,6 @@ def get_precision() -> str:
 # fold_upconv: True = always fold Blur o conv_transpose into one N = 4*Cout convolution; an int = only when Cin <= that value
 # (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 128, slower from Cin = 256 up:
 # tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
-import os as _os
 _options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])

@@ -153,6 +153,11 @@ typedef struct vt_conv_desc {
   const float* src_scale[2];    /* optional planar [B,H,W] per-pixel multiplier of source i, applied while the operand is split
                                  * (bf16x3 tensor-core mode, stride 1 only): conv(cat[f_G, f_E * m_E]) without materialising
                                  * f_E * m_E (model/vtoonify.py:127). Rejected by the other kernels.                        */
+  const float* src_affine[2];   /* optional [B][src_c[i]][2] = (scale, shift) per (sample, channel): in-image pixels of source i
+                                 * become x*scale + shift while the operand is split (bf16x3 tensor-core mode, stride 1 only);
+                                 * padding stays 0, exactly as the reference zero-pads the *normalised* tensor. Used to apply
+                                 * AdaIN (model/dualstylegan.py:16-21) inside the convolution that consumes it
+                                 * (vt_adain_affine_f32 builds the table). Rejected by the other kernels.                  */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */
@@ -217,6 +222,8 @@ int vt_fir_nhwc_f32(const float* in, const float* kernel, float* out, int B, int
 int64_t vt_instnorm_ws_bytes(int B, int64_t HW, int C, int mode);
 int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
                            float eps, float* stats, void* ws, void* stream);
+/* AdaIN as a per-(sample, channel) affine: affine[b][c] = (gamma*rstd, beta - gamma*mean*rstd); stats [B][Cs][2], gamma_beta [B][2*Cs] */
+int vt_adain_affine_f32(const float* stats, const float* gamma_beta, float* affine, int B, int Cs, void* stream);
 /* out[b,p,c] = gamma[b,c] * (x - mean) * rstd + beta[b,c]; gamma_beta: [B, 2*Cs] (gamma then beta) */
 int vt_adain_apply_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
                         const float* stats, const float* gamma_beta, float* out, int round_tf32, void* stream);

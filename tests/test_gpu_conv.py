@@ -568,3 +568,45 @@ def test_tc_epilogue_direct_global_stores(case, transpose):
         lib.vt_set_option(b"tc_direct_store", old[0]); lib.vt_set_option(b"tc_transpose", old[1])
         ops.set_precision(ops.DEFAULT_PRECISION)
     assert maxerr(y, ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item()), f"{maxerr(y, ref):.3e}"
+
+
+@pytest.mark.parametrize("transpose", [0, 2])
+@pytest.mark.parametrize("case", [(2, 64, 64, 19, 13, 3, 1, 1), (1, 512, 512, 9, 16, 3, 4, 4), (2, 128, 32, 24, 40, 3, 2, 2), (2, 64, 64, 9, 8, 1, 0, 1)])
+def test_bf16x3_per_channel_affine_on_source(case, transpose):
+    """conv(pad0(x*scale[b,c] + shift[b,c])) with the affine applied while tiles are split (AdaIN inside the consuming conv):
+    the zero padding must stay zero (the reference pads the normalised tensor), incl. dilated taps and the transposed view."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, pad, dil = case
+    g = torch.Generator().manual_seed(sum(case) + 43)
+    x = torch.randn((B, Cin, H, W), generator=g) * 2 + 0.5
+    aff = torch.randn((B, Cin, 2), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    xn = x * aff[:, :, 0, None, None] + aff[:, :, 1, None, None]
+    ref = F.conv2d(xn, w, b, padding=pad, dilation=dil)
+    lib = _lib.load()
+    old = lib.vt_set_option(b"tc_transpose", transpose)
+    ops.set_precision("bf16x3")
+    try:
+        y = ops.conv2d_nhwc([ops.to_nhwc(x.cuda())], ops.prep_weights(w.cuda(), cin_pad=Cin), ops.conv_taps(k, pad, dil), 1, H, W,
+                            bias=b.cuda(), src_affine=[aff.cuda()])
+        assert maxerr(ops.to_nchw(y).cpu(), ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())
+        with pytest.raises(_lib.VtError):
+            ops.conv2d_nhwc([ops.to_nhwc(x.cuda())], ops.prep_weights(w.cuda(), cin_pad=Cin), ops.conv_taps(k, pad, dil), 1, H, W,
+                            bias=b.cuda(), src_affine=[aff.cuda()], precision="fp32")
+    finally:
+        lib.vt_set_option(b"tc_transpose", old)
+        ops.set_precision(ops.DEFAULT_PRECISION)
+
+
+def test_adain_affine_table_vs_adain_apply():
+    from vtoonify_b200 import ops
+    g = torch.Generator().manual_seed(47)
+    x = torch.randn((2, 64, 11, 9), generator=g) * 1.5 + 0.3
+    gb = torch.randn((2, 128), generator=g)
+    xn = ops.to_nhwc(x.cuda())
+    st = ops.instnorm_stats(xn)
+    ref = ops.adain_apply(xn, st, gb.cuda())
+    aff = ops.adain_affine(st, gb.cuda())
+    y = xn * aff[:, None, None, :, 0] + aff[:, None, None, :, 1]
+    assert (y - ref).abs().max().item() <= 1e-5

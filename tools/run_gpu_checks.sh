@@ -20,7 +20,7 @@ run conv_tc_misc 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "ep
 run conv_tc_mt 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "m_tiles"
 run conv_tc_pairs 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "cta_pairs"
 run conv_tc_fold 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "folded"
-run conv_tc_bf16x3 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "bf16x3 or masked or tap_products or direct_global"
+run conv_tc_bf16x3 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "bf16x3 or masked or tap_products or direct_global or affine"
 run conv_tc_views 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "transposed_view"
 run layers 900 python -m pytest tests/test_gpu_layers.py -q -m gpu -s
 run vtoonify 900 python -m pytest tests/test_gpu_vtoonify.py -q -m gpu -s

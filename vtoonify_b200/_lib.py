@@ -35,7 +35,7 @@ class ConvDesc(Structure):
         ("round_tf32", c_int32), ("reserved", c_int32),
         ("rgb_w", c_void_p), ("rgb_bias", c_void_p), ("rgb_skip", c_void_p), ("rgb_skip_kernel", c_void_p),
         ("rgb_out", c_void_p),
-        ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("bf16x3_nstack", c_int32), ("reserved2", c_int32), ("src_scale", c_void_p * 2),
+        ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("bf16x3_nstack", c_int32), ("reserved2", c_int32), ("src_scale", c_void_p * 2), ("src_affine", c_void_p * 2),
     ]
 
 
@@ -84,6 +84,7 @@ SYMBOLS = {
                                 c_float, c_float, c_int, _P]),
     "vt_instnorm_ws_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),
     "vt_instnorm_stats_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "vt_adain_affine_f32": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vt_adain_apply_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, _P, _P, _P, c_int, _P]),
     "vt_gate_shortcut_add_nhwc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vt_bilinear_add_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -595,7 +595,8 @@ extern "C" int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream) {
   if (validate_conv_desc(d, "conv2d_direct")) return 1;
   VT_CHECK(d->B <= 65535 && vt_cdiv(d->Cout, BN) <= 65535, "conv2d_direct: grid too large");
   VT_CHECK(!d->rgb_w, "conv2d_direct: the fused ToRGB tail exists only in the tensor-core kernel");
-  VT_CHECK(!d->src_scale[0] && !d->src_scale[1], "conv2d_direct: src_scale is only implemented by the bf16x3 tensor-core kernel");
+  VT_CHECK(!d->src_scale[0] && !d->src_scale[1] && !d->src_affine[0] && !d->src_affine[1],
+           "conv2d_direct: src_scale / src_affine are only implemented by the bf16x3 tensor-core kernel");
   const int64_t HoWo = (int64_t)d->Ho * d->Wo;
   dim3 grid((unsigned)vt_cdiv(HoWo, BM), (unsigned)vt_cdiv(d->Cout, BN), (unsigned)d->B);
   for (int ph = 0; ph < d->n_phase; ++ph) {   // one launch per output phase (weight rows ph*Cout.., view offset phase_off[ph])

@@ -73,6 +73,8 @@ struct TcArgs {
   const float* rgb_w; const float* rgb_bias; const float* rgb_skip; const float* rgb_skip_kernel; float* rgb_out;
   const float* slope_vec;
   const float* src_scale[2]; // bf16x3: optional planar per-pixel multiplier of source s (kernel-space strides below)
+  const float* src_affine[2];  // bf16x3: optional [B][C_s][2] (scale, shift) applied to in-image pixels of source s
+  int src_cn[2];             // channels of source s (row length of src_affine)
   int64_t sc_sb, sc_sy, sc_sx;
   int in_w, in_h;            // kernel-space input extents
   int mma_n;                 // N of one MMA / TMEM columns per accumulator: block_n, or 2*block_n in the N-stacked bf16x3 form
@@ -336,7 +338,9 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       for (int s = 0; s < p.n_src; ++s) {
         const float* sc = p.src_scale[s];
+        const float* aff = p.src_affine[s];
         for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+          const float4* affp = aff ? reinterpret_cast<const float4*>(aff + ((int64_t)b * p.src_cn[s] + kc * KCH) * 2) : nullptr;
           const int loads = p.halo ? 1 : p.n_steps;
           for (int l = 0; l < loads; ++l) {
             VT_TWAIT(0, mbar_wait(a_full(a_st), a_par, 9));
@@ -352,13 +356,23 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(row + ((j ^ ph) << 4)));
                 f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
               }
-              if (sc) {   // per-pixel multiplier of this source (f_E * m_E): rows are box pixels in raster order
+              if (sc || aff) {   // rows are box pixels in raster order
                 const int ry = r / bw, rx = r - ry * bw;
                 const int ix = bx0 + rx, iy = by0 + ry;
-                const float mm = (ix >= 0 && ix < p.in_w && iy >= 0 && iy < p.in_h)
-                                     ? __ldg(sc + (int64_t)b * p.sc_sb + (int64_t)iy * p.sc_sy + (int64_t)ix * p.sc_sx) : 0.f;
+                const bool inb = ix >= 0 && ix < p.in_w && iy >= 0 && iy < p.in_h;
+                if (aff && inb) {   // per-(sample, channel) affine (AdaIN) on real pixels; the zero padding stays zero
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] *= mm;
+                  for (int j = 0; j < 16; ++j) {
+                    const float4 q = __ldg(affp + j);   // (scale, shift) of channels 2j, 2j+1 (same address in every thread)
+                    f[2 * j] = fmaf(f[2 * j], q.x, q.y);
+                    f[2 * j + 1] = fmaf(f[2 * j + 1], q.z, q.w);
+                  }
+                }
+                if (sc) {           // per-pixel multiplier of this source (f_E * m_E)
+                  const float mm = inb ? __ldg(sc + (int64_t)b * p.sc_sb + (int64_t)iy * p.sc_sy + (int64_t)ix * p.sc_sx) : 0.f;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] *= mm;
+                }
               }
               uint32_t hi[16], lo[16];
 #pragma unroll
@@ -661,7 +675,9 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP(d->out_sx % 4 == 0 && d->out_sy % 4 == 0 && d->out_sb % 4 == 0, "conv_tc: output strides must be multiples of 4 floats");
   VT_SUP(((uintptr_t)d->out & 15) == 0, "conv_tc: out not 16-byte aligned");
   VT_SUP(d->w_cstride % 4 == 0, "conv_tc: weight stride must be a multiple of 4");
-  VT_SUP((!d->src_scale[0] && !d->src_scale[1]) || (d->weight_bf16x3 && d->stride == 1), "conv_tc: src_scale needs the bf16x3 mode and stride 1");
+  VT_SUP((!d->src_scale[0] && !d->src_scale[1] && !d->src_affine[0] && !d->src_affine[1]) || (d->weight_bf16x3 && d->stride == 1),
+         "conv_tc: src_scale / src_affine need the bf16x3 mode and stride 1");
+  for (int s = 0; s < 2; ++s) VT_SUP(!d->src_affine[s] || (((uintptr_t)d->src_affine[s] & 15) == 0), "conv_tc: src_affine not 16-byte aligned");
   VT_SUP(!d->bf16x3_nstack || (d->weight_bf16x3 && d->Cout == 32 && d->n_phase == 1), "conv_tc: the N-stacked bf16x3 form needs Cout == 32 and one phase");
   VT_SUP(!d->weight_bf16x3 || d->w_cstride % KCH == 0, "conv_tc: bf16x3 weights need a channel stride that is a multiple of 32");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
@@ -739,6 +755,8 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.bf16x3 = d->weight_bf16x3 != nullptr;
   a.nstack = (a.bf16x3 && d->bf16x3_nstack) ? 1 : 0;
   a.src_scale[0] = d->src_scale[0]; a.src_scale[1] = d->src_scale[1];
+  a.src_affine[0] = d->src_affine[0]; a.src_affine[1] = d->src_affine[1];
+  a.src_cn[0] = d->src_c[0]; a.src_cn[1] = d->n_src > 1 ? d->src_c[1] : 0;
   a.in_w = gW; a.in_h = gH;
   a.sc_sb = (int64_t)d->H * d->W; a.sc_sy = T ? 1 : d->W; a.sc_sx = T ? d->W : 1;
 

@@ -317,6 +317,23 @@ extern "C" int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mod
   return 0;
 }
 
+__global__ void adain_affine_kernel(const float* __restrict__ stats, const float* __restrict__ gb, float* __restrict__ aff, int B, int Cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = b * Cs + c
+  if (i >= B * Cs) return;
+  const int b = i / Cs, c = i - b * Cs;
+  const float gamma = gb[(int64_t)b * 2 * Cs + c], beta = gb[(int64_t)b * 2 * Cs + Cs + c];
+  const float sc = gamma * stats[i * 2 + 1];
+  aff[i * 2] = sc;
+  aff[i * 2 + 1] = beta - sc * stats[i * 2];
+}
+
+extern "C" int vt_adain_affine_f32(const float* stats, const float* gamma_beta, float* affine, int B, int Cs, void* stream) {
+  VT_CHECK(stats && gamma_beta && affine && B >= 1 && Cs >= 1, "adain_affine: bad args");
+  adain_affine_kernel<<<(unsigned)vt_cdiv((int64_t)B * Cs, 128), 128, 0, (cudaStream_t)stream>>>(stats, gamma_beta, affine, B, Cs);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int vt_adain_apply_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
                                    const float* stats, const float* gamma_beta, float* out, int round_tf32, void* stream) {
   VT_CHECK(in && stats && gamma_beta && out && (mode == 0 || (mode == 1 && in2)), "adain_apply: bad pointers/mode");

@@ -42,7 +42,7 @@ def get_precision() -> str:
 # fold_upconv: True = always fold Blur o conv_transpose into one N = 4*Cout convolution; an int = only when Cin <= that value
 # (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 128, slower from Cin = 256 up:
 # tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
-_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False}
+_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False, "fuse_adain": True}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 
@@ -237,7 +237,8 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 noise_w: Optional[torch.Tensor] = None, act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0,
                 res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
                 precision: Optional[str] = None, rgb: Optional[dict] = None,
-                slope_vec: Optional[torch.Tensor] = None, src_scale: Optional[Sequence] = None) -> torch.Tensor:
+                slope_vec: Optional[torch.Tensor] = None, src_scale: Optional[Sequence] = None,
+                src_affine: Optional[Sequence] = None) -> torch.Tensor:
     """General NHWC convolution (virtual channel-concat of ``srcs``).
 
     ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
@@ -313,6 +314,14 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 if sc.numel() != B * H * W or not sc.is_contiguous():
                     raise _lib.VtError("conv2d_nhwc: src_scale must be a contiguous [B,H,W] map")
                 d.src_scale[i] = sc.data_ptr()
+    if src_affine is not None:
+        # per-(sample, channel) (scale, shift) table [B, C_i, 2] of a source (AdaIN applied inside the conv; bf16x3 mode only)
+        for i, af in enumerate(src_affine):
+            if af is not None:
+                _req_cuda(af)
+                if tuple(af.shape) != (B, int(d.src_c[i]), 2) or not af.is_contiguous():
+                    raise _lib.VtError("conv2d_nhwc: src_affine must be a contiguous [B, C, 2] table")
+                d.src_affine[i] = af.data_ptr()
     lib = _lib.load()
     if prec == "bf16x3":
         d.weight_bf16x3 = weight.data_ptr()   # marks the mode for vt_conv2d_tc_supported; the split buffer is attached below
@@ -359,6 +368,11 @@ def split_weights_bf16x3(weight: torch.Tensor, nstack: bool = False) -> torch.Te
     check(_lib.load().vt_split_weights_bf16x3(weight.data_ptr(), out.data_ptr(), rows, weight.shape[-1], nrows, _stream()))
     weight._vt_bf16x3 = (ver, weight.data_ptr(), out, nstack)
     return out
+
+
+def affine_fusable(precision: Optional[str] = None) -> bool:
+    """conv2d_nhwc(src_affine=...) is available and enabled (AdaIN applied by the operand-transform warps)."""
+    return (precision or _precision) == "bf16x3" and _options["fuse_adain"]
 
 
 def scale_fusable(precision: Optional[str] = None) -> bool:
@@ -523,6 +537,17 @@ def instnorm_stats(x: torch.Tensor, x2: Optional[torch.Tensor] = None, eps: floa
     check(_lib.load().vt_instnorm_stats_nhwc(x.data_ptr(), _ptr(x2), mode, B, H * W, C, C, eps, stats.data_ptr(),
                                              ws.data_ptr(), _stream()))
     return stats
+
+
+def adain_affine(stats: torch.Tensor, gamma_beta: torch.Tensor) -> torch.Tensor:
+    """AdaIN as a per-(sample, channel) affine table ``[B, Cs, 2]`` = (gamma*rstd, beta - gamma*mean*rstd) for
+    ``conv2d_nhwc(src_affine=...)`` (model/dualstylegan.py:16-21 applied inside the consuming convolution)."""
+    _req_cuda(stats, gamma_beta)
+    B, Cs, _ = stats.shape
+    out = torch.empty((B, Cs, 2), device=stats.device, dtype=torch.float32)
+    check(_lib.load().vt_adain_affine_f32(stats.contiguous().data_ptr(), gamma_beta.contiguous().data_ptr(), out.data_ptr(), B, Cs,
+                                          _stream()))
+    return out
 
 
 def adain_apply(x: torch.Tensor, stats: torch.Tensor, gamma_beta: torch.Tensor, x2: Optional[torch.Tensor] = None) -> torch.Tensor:

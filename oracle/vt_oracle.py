@@ -303,3 +303,66 @@ def psp_forward(sd, x, n_styles=18):
     p1 = F.interpolate(p2, size=c1.shape[2:], mode="bilinear", align_corners=True) + F.conv2d(c1, sd["latlayer2.weight"], sd["latlayer2.bias"])
     lat += [head(j, p1) for j in range(7, n_styles)]
     return torch.stack(lat, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# f (next row): BiSeNet face parsing as the frame loop uses it   (model/bisenet/model.py:17-259, resnet.py:20-83,
+# style_transfer.py:165-174)
+# ------------------------------------------------------------------------------------------------
+def _cbr(x, sd, p, stride=1, padding=1):
+    """ConvBNReLU (model/bisenet/model.py:17-34)."""
+    return F.relu(_bn(F.conv2d(x, sd[p + "conv.weight"], stride=stride, padding=padding), sd, p + "bn."))
+
+
+def _basic_block(x, sd, p):
+    """resnet.py:20-47: relu(shortcut + bn2(conv2(relu(bn1(conv1 x))))); a 1x1 stride-2 conv + BN shortcut exists in the
+    state_dict exactly for the blocks that change channels and resolution."""
+    has_ds = (p + "downsample.0.weight") in sd
+    stride = 2 if has_ds else 1      # Resnet18 (resnet.py:58-61): the first block of layers 2-4 halves the resolution
+    r = F.relu(_bn(F.conv2d(x, sd[p + "conv1.weight"], stride=stride, padding=1), sd, p + "bn1."))
+    r = _bn(F.conv2d(r, sd[p + "conv2.weight"], padding=1), sd, p + "bn2.")
+    sc = x
+    if has_ds:
+        sc = _bn(F.conv2d(x, sd[p + "downsample.0.weight"], stride=stride), sd, p + "downsample.1.")
+    return F.relu(sc + r)
+
+
+def _arm(x, sd, p):
+    """AttentionRefinementModule (model.py:63-84)."""
+    feat = _cbr(x, sd, p + "conv.")
+    att = F.avg_pool2d(feat, feat.shape[2:])
+    att = torch.sigmoid(_bn(F.conv2d(att, sd[p + "conv_atten.weight"]), sd, p + "bn_atten."))
+    return feat * att
+
+
+def bisenet_forward(sd, x):
+    """BiSeNet(n_classes).forward in eval mode -> feat_out only (the frame loop uses output [0]); x: [B,3,H,W]."""
+    H, W = x.shape[2:]
+    r = "cp.resnet."
+    h = F.relu(_bn(F.conv2d(x, sd[r + "conv1.weight"], stride=2, padding=3), sd, r + "bn1."))
+    h = F.max_pool2d(h, 3, 2, 1)
+    feats = []
+    for layer in (1, 2, 3, 4):
+        for blk in (0, 1):
+            h = _basic_block(h, sd, f"{r}layer{layer}.{blk}.")
+        feats.append(h)
+    feat8, feat16, feat32 = feats[1], feats[2], feats[3]
+    avg = _cbr(F.avg_pool2d(feat32, feat32.shape[2:]), sd, "cp.conv_avg.", padding=0)
+    f32 = _arm(feat32, sd, "cp.arm32.") + F.interpolate(avg, feat32.shape[2:], mode="nearest")
+    f32_up = _cbr(F.interpolate(f32, feat16.shape[2:], mode="nearest"), sd, "cp.conv_head32.")
+    f16 = _arm(feat16, sd, "cp.arm16.") + f32_up
+    f16_up = _cbr(F.interpolate(f16, feat8.shape[2:], mode="nearest"), sd, "cp.conv_head16.")
+    # FeatureFusionModule(feat_sp = feat8, feat_cp8 = f16_up)  (model.py:187-213, 237-239)
+    feat = _cbr(torch.cat([feat8, f16_up], 1), sd, "ffm.convblk.", padding=0)
+    att = F.avg_pool2d(feat, feat.shape[2:])
+    att = torch.sigmoid(F.conv2d(F.relu(F.conv2d(att, sd["ffm.conv1.weight"])), sd["ffm.conv2.weight"]))
+    fuse = feat * att + feat
+    out = F.conv2d(_cbr(fuse, sd, "conv_out.conv."), sd["conv_out.conv_out.weight"])
+    return F.interpolate(out, (H, W), mode="bilinear", align_corners=True)
+
+
+def parsing_for_vtoonify(sd, frames):
+    """style_transfer.py:171-174: parsing logits of the 2x-upsampled frame, taken back to frame size by nearest sampling;
+    the caller concatenates ``cat(frames, x_p / 16)``.  frames: [B,3,H,W] in [-1,1]."""
+    x2 = 2 * F.interpolate(frames, scale_factor=2, mode="bilinear", align_corners=False)
+    return F.interpolate(bisenet_forward(sd, x2), scale_factor=0.5, recompute_scale_factor=False)

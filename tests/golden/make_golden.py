@@ -191,9 +191,29 @@ def golden_psp():
     save("psp", x=x.half(), y=y)
 
 
+def golden_bisenet():
+    """Face-parsing maps as the frame loop builds them (style_transfer.py:171-174). The reference constructor downloads
+    ResNet-18 weights; here model_zoo.load_url is stubbed (no network) and every tensor comes from det_state_dict."""
+    import torch.nn.functional as F
+    import torch.utils.model_zoo as mz
+    mz.load_url = lambda *a, **k: {}
+    from model.bisenet.model import BiSeNet
+    m = BiSeNet(n_classes=19).eval()
+    keys = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_keys_bisenet.json"), "w") as f:
+        json.dump(keys, f, indent=0)
+    m.load_state_dict(det_state_dict(m, seed=21), strict=True)
+    x = (torch.rand((2, 3, 64, 96), generator=gen(3)) * 2 - 1).half().float()
+    x_p = F.interpolate(m(2 * F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))[0], scale_factor=0.5,
+                        recompute_scale_factor=False)
+    print("bisenet", tuple(x_p.shape), "rms %.3f" % x_p.pow(2).mean().sqrt())
+    save("bisenet", x=x.half(), x_p=x_p)
+
+
 if __name__ == "__main__":
     golden_ops()
     golden_layers()
     golden_generator()
     golden_vtoonify()
     golden_psp()
+    golden_bisenet()

@@ -131,3 +131,16 @@ def test_psp_encoder_golden(golden):
     y = O.psp_forward(sd, T(g["x"]).float())
     ref = T(g["y"])
     assert_close(y, ref, 1e-4 * ref.abs().max().item(), "pSp encoder")
+
+
+def test_bisenet_parsing_golden(golden):
+    """Next row (f): BiSeNet parsing maps of the frame loop (2x bilinear up-sampling, BiSeNet, nearest back to frame size),
+    restated functionally from the state_dict, vs the reference module's output."""
+    g = golden("bisenet")
+    keys = json.load(open("tests/golden/state_dict_keys_bisenet.json"))
+    sd = det_state_dict({k: torch.empty(v, dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+                         for k, v in keys.items()}, seed=21)
+    y = O.parsing_for_vtoonify(sd, T(g["x"]).float())
+    ref = T(g["x_p"])
+    assert tuple(y.shape) == (2, 19, 64, 96)
+    assert_close(y, ref, 1e-4 * ref.abs().max().item(), "BiSeNet parsing maps")

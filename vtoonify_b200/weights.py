@@ -25,6 +25,10 @@ def det_tensor(key: str, ref: torch.Tensor, seed: int = 0) -> torch.Tensor:
         return 0.2 * (1.0 + 0.1 * r)                            # last BN of a residual branch: small gamma keeps the 24-block
                                                                  # IR stack well conditioned (gamma ~ 1 makes it chaotic: a 1e-7
                                                                  # perturbation grows 1.8x per block, measured)
+    if ref.dim() == 1 and re.search(r"(^|\.)bn2\.weight$", key):
+        return 0.5 * (1.0 + 0.1 * r)                            # BiSeNet / ResNet-18: last BN of a residual branch
+    if ref.dim() == 1 and re.search(r"(^|\.)(bn\d*|bn_atten|downsample\.1)\.weight$", key):
+        return 1.0 + 0.1 * r                                    # BiSeNet BatchNorm gamma
     if ref.dim() == 1 and re.search(r"(input_layer\.1|res_layer\.0|shortcut_layer\.1)\.weight$", key):
         return 1.0 + 0.1 * r                                    # BatchNorm gamma
     if ref.dim() == 1 and re.search(r"(input_layer\.2|res_layer\.2)\.weight$", key):

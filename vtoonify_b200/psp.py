@@ -19,8 +19,8 @@ import torch
 from torch import nn
 
 from . import ops
-from ._lib import ACT_LRELU, ACT_NONE
-from .stylegan import EqualLinear, _PreppedWeight
+from ._lib import ACT_LRELU
+from .stylegan import EqualLinear
 from .vtoonify import Conv2d
 
 

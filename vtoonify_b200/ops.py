@@ -329,8 +329,8 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     d.weight_bf16x3 = None
     if use_tc and prec == "bf16x3":
         # Cout == 32: the N-stacked form needs 4 instead of 6 MMA instructions per tap (and keeps all four hi/lo products);
-        # measured on B200 it is no faster (N = 64 MMAs take ~1.5x the time of N = 32 ones: these layers are bound by the
-        # shared-memory operand reads of the MMAs, not by instruction issue), so it is off by default
+        # measured on B200 it is no faster end to end (the epilogue's second TMEM load + add becomes the limiter: DESIGN.md
+        # section 4), so it is off by default
         nstack = bool(_options["bf16x3_nstack"]) and Cout == 32 and phase_offs is None
         d.weight_bf16x3 = split_weights_bf16x3(weight, nstack).data_ptr()
         d.bf16x3_nstack = 1 if nstack else 0

@@ -237,6 +237,20 @@ int vt_gate_shortcut_add_nhwc(const float* x, const float* gate, const float* sc
 int vt_bilinear_add_nhwc(const float* x, const float* y, float* out, int B, int h, int w, int H, int W, int C,
                          int round_tf32, void* stream);
 
+/* ---- face-parsing pre-network helpers (model/bisenet/model.py, style_transfer.py:171-174; next row of SURVEY 8f) ---- */
+/* Space-to-depth input of the stride-2 7x7 stem: out[b,y,x,(py*2+px)*3+c] = X[b,c,2y+py,2x+px] (zero beyond X and in the pad
+ * channels), X = in (upsample2 = 0) or 2 * F.interpolate(in, scale_factor=2, 'bilinear', align_corners=False) (upsample2 = 1).
+ * in: planar [B,3,Hin,Win]; out: NHWC [B,Ho,Wo,cpad], Ho = ceil(XH/2). A 7x7/2 conv on X is a 4x4/1 conv on this tensor. */
+int vt_frame_s2d_f32(const float* in, float* out, int B, int Hin, int Win, int Ho, int Wo, int cpad, int upsample2, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on NHWC: out [B, (H-1)/2+1, (W-1)/2+1, C] */
+int vt_maxpool3x3s2_nhwc_f32(const float* in, float* out, int B, int H, int W, int C, void* stream);
+/* F.interpolate(in, (H, W), mode='nearest') on NHWC */
+int vt_resize_nearest_nhwc_f32(const float* in, float* out, int B, int h, int w, int H, int W, int C, void* stream);
+/* out[b,c,y,x] = scale * F.interpolate(logits, (Hf, Wf), 'bilinear', align_corners=True)[b, c, step*y, step*x];
+ * logits: NHWC [B,h,w,c_stride] (first n_classes channels used); out: planar [B,n_classes,Ho,Wo] */
+int vt_logits_readout_f32(const float* in, float* out, int B, int h, int w, int c_stride, int n_classes, int Hf, int Wf,
+                          int Ho, int Wo, int step, float scale, void* stream);
+
 /* ---- elementwise helpers ------------------------------------------------------------------ */
 /* out = a * scale_a + b * scale_b (b may be NULL) */
 int vt_axpby_f32(const float* a, const float* b, float* out, int64_t n, float scale_a, float scale_b, int round_tf32, void* stream);

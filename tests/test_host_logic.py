@@ -152,3 +152,43 @@ def test_precision_and_algorithm_switches():
         assert ops.use_folded_upconv(512)
     finally:
         ops.set_option("fold_upconv", thr)
+
+
+def test_bisenet_state_dict_keys_and_host_algebra():
+    """Next row (f): the BiSeNet module has the reference's 191 keys / shapes, and its host-side weight algebra is exact:
+    (1) the stride-2 7x7 stem equals a stride-1 4x4 convolution over the space-to-depth tensor with the re-indexed weights
+    and tap list the module feeds to the tensor-core kernel, (2) conv + eval BatchNorm equals the folded conv + bias."""
+    import json
+    import torch
+    import torch.nn.functional as F
+    from vtoonify_b200.bisenet import BiSeNet, S2D_TAPS, fold_bn, s2d_stem_weight
+    from vtoonify_b200.psp import BatchNorm2d
+    m = BiSeNet(19)
+    keys = json.load(open("tests/golden/state_dict_keys_bisenet.json"))
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(keys.keys()) and all(list(sd[k].shape) == keys[k] for k in keys)
+
+    g = torch.Generator().manual_seed(0)
+    for (H, W) in ((12, 16), (11, 15)):                       # even and odd sizes (zero rows beyond X)
+        x = torch.randn((2, 3, H, W), generator=g)
+        w7 = torch.randn((5, 3, 7, 7), generator=g)
+        ref = F.conv2d(x, w7, stride=2, padding=3)
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        xp = F.pad(x, (0, 2 * Wo - W, 0, 2 * Ho - H))
+        z = torch.stack([xp[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], dim=1).reshape(2, 12, Ho, Wo)
+        w4 = s2d_stem_weight(w7)
+        # evaluate exactly what the kernel is asked for: out[oy,ox] = sum_t sum_c z[oy+dy_t, ox+dx_t, c] * w4[:, c, slab_t]
+        zp = F.pad(z, (2, 2, 2, 2))
+        out = torch.zeros_like(ref)
+        for dy, dx, t in S2D_TAPS:
+            patch = zp[:, :, 2 + dy:2 + dy + Ho, 2 + dx:2 + dx + Wo]
+            out += torch.einsum("bchw,nc->bnhw", patch, w4[:, :, t // 4, t % 4])
+        assert out.shape == ref.shape and (out - ref).abs().max().item() <= 1e-4
+
+    bn = BatchNorm2d(6)
+    bn.weight.data = torch.randn(6, generator=g); bn.bias.data = torch.randn(6, generator=g)
+    bn.running_mean = torch.randn(6, generator=g); bn.running_var = torch.rand(6, generator=g) + 0.5
+    w = torch.randn((6, 4, 3, 3), generator=g); x = torch.randn((1, 4, 9, 9), generator=g)
+    ref = F.batch_norm(F.conv2d(x, w, padding=1), bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, 1e-5)
+    wf, bf = fold_bn(w, bn)
+    assert (F.conv2d(x, wf, bf, padding=1) - ref).abs().max().item() <= 1e-5

@@ -84,6 +84,10 @@ SYMBOLS = {
                                 c_float, c_float, c_int, _P]),
     "vt_instnorm_ws_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),
     "vt_instnorm_stats_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "vt_frame_s2d_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "vt_maxpool3x3s2_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "vt_resize_nearest_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "vt_logits_readout_f32": (c_int, [_P, _P] + [c_int] * 10 + [c_float, _P]),
     "vt_adain_affine_f32": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vt_adain_apply_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, _P, _P, _P, c_int, _P]),
     "vt_gate_shortcut_add_nhwc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -623,3 +623,49 @@ def f32_to_frames_u8(img: torch.Tensor, swap_rb: bool = True) -> torch.Tensor:
     out = torch.empty((B, H, W, 3), device=img.device, dtype=torch.uint8)
     check(_lib.load().vt_f32_to_frame_u8(img.contiguous().data_ptr(), out.data_ptr(), B, H, W, int(swap_rb), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# face-parsing pre-network helpers (model/bisenet/model.py, style_transfer.py:171-174)
+# ----------------------------------------------------------------------------------------------
+def frame_s2d(x: torch.Tensor, upsample2: bool, cpad: int = 32) -> torch.Tensor:
+    """planar ``[B,3,H,W]`` -> NHWC space-to-depth tensor ``[B, ceil(XH/2), ceil(XW/2), cpad]`` of X = x (or of
+    ``2 * bilinear_up2(x)``), the input of the stride-2 7x7 stem run as a 4x4 stride-1 convolution."""
+    _req_cuda(x)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    if C != 3:
+        raise _lib.VtError("frame_s2d: expected 3 planar channels")
+    XH, XW = (2 * H, 2 * W) if upsample2 else (H, W)
+    out = torch.empty((B, (XH + 1) // 2, (XW + 1) // 2, cpad), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_frame_s2d_f32(x.data_ptr(), out.data_ptr(), B, H, W, out.shape[1], out.shape[2], cpad, int(bool(upsample2)),
+                                       _stream()))
+    return out
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    _req_cuda(x)
+    B, H, W, C = x.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_maxpool3x3s2_nhwc_f32(x.contiguous().data_ptr(), out.data_ptr(), B, H, W, C, _stream()))
+    return out
+
+
+def resize_nearest(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    _req_cuda(x)
+    B, h, w, C = x.shape
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+    check(_lib.load().vt_resize_nearest_nhwc_f32(x.contiguous().data_ptr(), out.data_ptr(), B, h, w, H, W, C, _stream()))
+    return out
+
+
+def logits_readout(logits: torch.Tensor, n_classes: int, Hf: int, Wf: int, step: int = 1, scale: float = 1.0) -> torch.Tensor:
+    """NHWC logits ``[B,h,w,Cs]`` -> planar ``[B,n_classes,ceil(Hf/step),ceil(Wf/step)]``: every ``step``-th pixel of the
+    ``align_corners=True`` bilinear up-sampling to ``(Hf, Wf)``."""
+    _req_cuda(logits)
+    B, h, w, Cs = logits.shape
+    Ho, Wo = (Hf + step - 1) // step, (Wf + step - 1) // step
+    out = torch.empty((B, n_classes, Ho, Wo), device=logits.device, dtype=torch.float32)
+    check(_lib.load().vt_logits_readout_f32(logits.contiguous().data_ptr(), out.data_ptr(), B, h, w, Cs, n_classes, Hf, Wf, Ho, Wo,
+                                            step, float(scale), _stream()))
+    return out

@@ -34,7 +34,8 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 2   /* 2: vt_conv_desc gained weight_bf16x3 / bf16x3_nstack / src_scale, vt_smalln_desc src_mask / tsum, vt_split_weights_bf16x3 */
+#define VT_ABI_VERSION 3   /* 2: vt_conv_desc gained weight_bf16x3 / bf16x3_nstack / src_scale, vt_smalln_desc src_mask / tsum, vt_split_weights_bf16x3
+                            * 3: face-parsing helpers (vt_frame_s2d_f32 .. vt_logits_readout_f32 with out_bstride), backward ops, frame pre-filter */
 
 /* ---- library info / errors ------------------------------------------------------------- */
 int         vt_abi_version(void);
@@ -247,9 +248,10 @@ int vt_maxpool3x3s2_nhwc_f32(const float* in, float* out, int B, int H, int W, i
 /* F.interpolate(in, (H, W), mode='nearest') on NHWC */
 int vt_resize_nearest_nhwc_f32(const float* in, float* out, int B, int h, int w, int H, int W, int C, void* stream);
 /* out[b,c,y,x] = scale * F.interpolate(logits, (Hf, Wf), 'bilinear', align_corners=True)[b, c, step*y, step*x];
- * logits: NHWC [B,h,w,c_stride] (first n_classes channels used); out: planar [B,n_classes,Ho,Wo] */
+ * logits: NHWC [B,h,w,c_stride] (first n_classes channels used); out: planar [B,n_classes,Ho,Wo] with `out_bstride`
+ * elements between samples (0 = dense), so the frame loop can write channels 3..21 of its [B,22,H,W] network input in place */
 int vt_logits_readout_f32(const float* in, float* out, int B, int h, int w, int c_stride, int n_classes, int Hf, int Wf,
-                          int Ho, int Wo, int step, float scale, void* stream);
+                          int Ho, int Wo, int step, float scale, int64_t out_bstride, void* stream);
 
 /* ---- elementwise helpers ------------------------------------------------------------------ */
 /* out = a * scale_a + b * scale_b (b may be NULL) */

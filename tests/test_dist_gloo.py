@@ -45,3 +45,52 @@ def test_scatter_gather_world2(nb):
     for p in procs:
         p.join(timeout=60)
     assert res == {0: True, 1: True}
+
+
+def _loop_worker(rank, world, port, nb, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vtoonify_b200.frame_loop import ShardedFrameLoop, shard_indices
+    in_shape, out_shape = (2, 6, 5, 3), (2, 12, 10, 3)
+
+    def batch(i):
+        return (torch.arange(2 * 6 * 5 * 3, dtype=torch.float32).reshape(in_shape) + 100.0 * i) % 251
+
+    def fn(x):                                  # stands for assemble + synthesize: any per-batch function of the inputs
+        return x.repeat_interleave(2, 1).repeat_interleave(2, 2).to(torch.uint8)
+
+    got, staged = {}, []
+    loop = ShardedFrameLoop(fn, in_shape, torch.float32, out_shape, torch.uint8, "cpu")
+
+    def stage(i):
+        staged.append(i)
+        return batch(i)
+
+    def sink(i, buf, ready):
+        ready()
+        got[i] = buf.clone()
+
+    mine = loop.run(nb, stage=stage if rank == 0 else None, sink=sink if rank == 0 else None)
+    ok = mine == len(shard_indices(nb, rank, world))
+    if rank == 0:
+        ok = ok and staged == list(range(nb)) and sorted(got) == list(range(nb))
+        ok = ok and all(torch.equal(got[i], fn(batch(i))) for i in range(nb))
+        ok = ok and loop.scatter_bytes > 0 and loop.gather_bytes > 0
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nb", [1, 4, 7])
+def test_sharded_frame_loop_world2(nb):
+    """rank-0 clip -> per-round scatter -> per-rank function -> gather, double-buffered, results in clip order"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loop_worker, args=(r, 2, port, nb, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}

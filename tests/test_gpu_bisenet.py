@@ -1,14 +1,10 @@
-"""GPU parity of the BiSeNet parsing path (next row of SURVEY 8f) against the reference outputs in tests/golden/bisenet.npz.
-Written in round 1 after the GPU budget was spent: opt-in (VT_TEST_BISENET=1) until it has run green on a B200 once."""
-import json
-import os
-
+"""GPU parity of the BiSeNet parsing path (style_transfer.py:171-172, model/bisenet/model.py:230-254) against
+the reference outputs in tests/golden/bisenet.npz and against the CPU oracle."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("VT_TEST_BISENET") != "1",
-                                                  reason="BiSeNet CUDA path not yet validated on a B200 (set VT_TEST_BISENET=1)")]
+pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
 

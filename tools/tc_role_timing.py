@@ -28,13 +28,17 @@ def report(name, fn, flops):
           f" | xform tma-wait {pct(15):4.1f}")
 
 
-def conv_case(B, Cin, Cout, H, W, k=3, dil=1):
+def conv_case(B, Cin, Cout, H, W, k=3, dil=1, rgb=False):
     x = torch.randn((B, H, W, Cin), device=dev)
     w = ops.prep_weights(torch.randn((Cout, Cin, k, k), device=dev) / (3 * Cin ** 0.5), cin_pad=Cin)
     bias = torch.zeros(Cout, device=dev)
     pad = dil * (k // 2)
-    fn = lambda: ops.conv2d_nhwc([x], w, ops.conv_taps(k, pad, dil), 1, H, W, bias=bias, act=1)
-    report(f"{Cin}->{Cout} k{k} d{dil} {H}x{W} B{B}", fn, 2.0 * B * H * W * Cout * Cin * k * k)
+    r = None
+    if rgb:   # fused ToRGB tail with the skip image (what conv2 of every generator level carries)
+        r = {"w": torch.randn((B, 1, 3, Cout), device=dev) * 0.1, "bias": torch.zeros(3, device=dev),
+             "skip": torch.randn((B, 3, H // 2, W // 2), device=dev), "kernel": K4}
+    fn = lambda: ops.conv2d_nhwc([x], w, ops.conv_taps(k, pad, dil), 1, H, W, bias=bias, act=1, rgb=r)
+    report(f"{Cin}->{Cout} k{k} d{dil} {H}x{W} B{B}{' +rgb' if rgb else ''}", fn, 2.0 * B * H * W * Cout * Cin * k * k)
 
 
 def up_case(B, Cin, Cout, H, W):
@@ -54,9 +58,18 @@ with torch.no_grad():
     conv_case(4, 128, 128, 576, 1024)
     conv_case(4, 64, 64, 1152, 2048)
     conv_case(4, 32, 32, 2304, 4096)
+    conv_case(4, 32, 32, 2304, 4096, rgb=True)
+    conv_case(4, 64, 64, 1152, 2048, rgb=True)
     up_case(4, 64, 32, 1152, 2048)
     up_case(4, 128, 64, 576, 1024)
     up_case(4, 512, 256, 144, 256)
     conv_case(4, 256, 128, 576, 1024)
     conv_case(4, 128, 32, 576, 1024, k=1)
     conv_case(4, 128, 256, 288, 512, k=3)
+
+out = torch.zeros(4, device=dev)
+for mode, name in ((0, "ld x32 + wait"), (1, "4 x ld x32, one wait"), (2, "st x32 + wait"), (3, "4 x st x32, one wait")):
+    _lib.check(lib.vt_selftest_tc_gemm(None, None, out.data_ptr(), 0, mode, 2000, 64, None))
+    torch.cuda.synchronize()
+    print(f"TMEM probe {name:22s}: {out[0].item():7.1f} cycles per 32-column access per warp (4 warps active) "
+          f"= {128 * 32 * 4 / max(out[0].item(), 1e-9):7.1f} B/clk/SM")

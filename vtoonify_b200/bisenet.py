@@ -9,9 +9,9 @@ same constructor and state_dict keys (191) as the reference, running on the pack
 * the final ``align_corners=True`` up-sampling and the frame loop's nearest x0.5 are one read-out kernel that only evaluates
   the pixels that survive.
 
-STATUS (round 1): the host-side algebra below (BN folding, stem re-indexing) is checked on the CPU against torch
-(tests/test_host_logic.py) and the oracle restatement is pinned to the reference (tests/golden/bisenet.npz); the GPU parity
-test (tests/test_gpu_bisenet.py) has not been run on a B200 yet and is therefore opt-in (VT_TEST_BISENET=1).
+The host-side algebra below (BN folding, stem re-indexing) is checked on the CPU against torch (tests/test_host_logic.py), the
+oracle restatement is pinned to the reference (tests/golden/bisenet.npz) and tests/test_gpu_bisenet.py checks the CUDA path
+against both.
 """
 import torch
 from torch import nn
@@ -275,9 +275,10 @@ class BiSeNet(nn.Module):
         return tuple(ops.logits_readout(head.logits_nhwc(f), self.n_classes, H, W)
                      for head, f in ((self.conv_out, fuse), (self.conv_out16, cp8), (self.conv_out32, cp16)))
 
-    def parsing_for_frames(self, frames, scale=1.0):
+    def parsing_for_frames(self, frames, scale=1.0, out=None):
         """frames [B,3,H,W] in [-1,1] -> ``scale * x_p`` [B,n_classes,H,W] with
-        x_p = F.interpolate(self(2 * F.interpolate(frames, scale_factor=2, mode='bilinear'))[0], scale_factor=0.5)."""
+        x_p = F.interpolate(self(2 * F.interpolate(frames, scale_factor=2, mode='bilinear'))[0], scale_factor=0.5)
+        (style_transfer.py:171-172).  ``out``: optional channel slice of the network input (``inputs[:, 3:]``) to fill in place."""
         H, W = frames.shape[2:]
         fuse, _, _ = self._features(ops.frame_s2d(frames, upsample2=True))
-        return ops.logits_readout(self.conv_out.logits_nhwc(fuse), self.n_classes, 2 * H, 2 * W, step=2, scale=scale)
+        return ops.logits_readout(self.conv_out.logits_nhwc(fuse), self.n_classes, 2 * H, 2 * W, step=2, scale=scale, out=out)

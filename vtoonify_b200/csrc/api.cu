@@ -29,9 +29,9 @@ extern "C" {
 int vt_abi_version(void) { return VT_ABI_VERSION; }
 const char* vt_last_error(void) { return g_err; }
 const char* vt_build_info(void) {
-  return "libvtoonify_b200 abi=1 arch=sm_100a cuda="
 #define VT_STR2(x) #x
 #define VT_STR(x) VT_STR2(x)
+  return "libvtoonify_b200 abi=" VT_STR(VT_ABI_VERSION) " arch=sm_100a cuda="
       VT_STR(__CUDACC_VER_MAJOR__) "." VT_STR(__CUDACC_VER_MINOR__) " built " __DATE__;
 }
 int64_t vt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -10,7 +10,7 @@ SRCS="api.cu upfirdn2d.cu elementwise.cu modulate.cu conv_direct.cu norm_fir.cu 
 OBJS=""
 pids=()
 for s in $SRCS; do
-  [ -f "$HERE/$s" ] || continue
+  [ -f "$HERE/$s" ] || { echo "build.sh: missing source $HERE/$s" >&2; exit 1; }
   o="$OUT/${s%.cu}.o"
   if [ ! -f "$o" ] || [ "$HERE/$s" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/vtoonify_b200.h" -nt "$o" ] || [ "$HERE/tc_common.cuh" -nt "$o" ]; then
     $NVCC $FLAGS ${VT_PTXAS_V:+-Xptxas -v} -c "$HERE/$s" -o "$o" &

@@ -1065,7 +1065,86 @@ tc_issue_bench_kernel(float* out, const float* scratch, int N, int reps, int var
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ---- TMEM access-rate probe (tuning aid): 4 warps (one per lane quadrant) run `reps` rounds of 4 x tcgen05.ld / tcgen05.st of
+// 32 columns each. mode 0: ld + wait after every load; 1: 4 loads in flight, one wait; 2: st (zeros) + wait::st per store;
+// 3: 4 stores, one wait. out[0] = cycles per 32-column access of one warp with all 4 warps active.
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_zero_32x32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__global__ void __launch_bounds__(128, 1)
+tmem_probe_kernel(float* out, int reps, int mode) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) { tmem_alloc(smem_u32(&slot), 512); tc_fence_before(); }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot + ((uint32_t)(warp * 32) << 16);
+  for (int c = 0; c < 512; c += 32) tmem_st_zero_32x32(tmem + c);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  __syncthreads();
+  uint32_t acc = 0;
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    if (mode == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t v[32];
+        tmem_ld_32x32_nowait(tmem + (uint32_t)(((r * 4 + k) & 15) * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        acc += v[lane];
+      }
+    } else if (mode == 1) {
+      uint32_t v0[32], v1[32], v2[32], v3[32];
+      tmem_ld_32x32_nowait(tmem + (uint32_t)(((r * 4 + 0) & 15) * 32), v0);
+      tmem_ld_32x32_nowait(tmem + (uint32_t)(((r * 4 + 1) & 15) * 32), v1);
+      tmem_ld_32x32_nowait(tmem + (uint32_t)(((r * 4 + 2) & 15) * 32), v2);
+      tmem_ld_32x32_nowait(tmem + (uint32_t)(((r * 4 + 3) & 15) * 32), v3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += v0[lane] + v1[(lane + 1) & 31] + v2[(lane + 2) & 31] + v3[(lane + 3) & 31];
+    } else if (mode == 2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        tmem_st_zero_32x32(tmem + (uint32_t)(((r * 4 + k) & 15) * 32));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tmem_st_zero_32x32(tmem + (uint32_t)(((r * 4 + k) & 15) * 32));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (float)(t1 - t0) / (float)(reps * 4);
+  if (acc == 0xdeadbeefu) out[1] = 1.f;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
+}
+
 extern "C" int vt_selftest_tc_gemm(const float* A, const float*, float* D, int, int N, int K, int variant, void* stream) {
+  if (variant & 64) {   // TMEM access-rate probe: N = mode (0..3), K = reps
+    VT_CHECK(D && K >= 1 && N >= 0 && N <= 3, "selftest_tc_gemm: TMEM probe needs D, reps >= 1, mode 0..3");
+    tmem_probe_kernel<<<vt_num_sms(), 128, 0, (cudaStream_t)stream>>>(D, K, N);
+    VT_LAUNCH_CHECK();
+    return 0;
+  }
   VT_CHECK(D && N >= 16 && N <= 256 && N % 16 == 0 && K >= 1, "selftest_tc_gemm: D (device float[2]) / N / reps invalid");
   VT_CHECK(!(variant & 32) || A, "selftest_tc_gemm: variant bit 5 needs a scratch buffer A of 148*48 KB");
   const int smem = 3 * (24576 + 32768) + 1024 + 49152 + 1024;

@@ -99,7 +99,7 @@ resize_nearest_kernel(const float* __restrict__ in, float* __restrict__ out, int
 // step 2 = the frame loop's nearest x0.5 of the 2x-size parsing map (style_transfer.py:171-172) without materialising it.
 __global__ void __launch_bounds__(256)
 logits_readout_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int cs, int ncls, int Hf, int Wf,
-                      int Ho, int Wo, int step, float scale) {
+                      int Ho, int Wo, int step, float scale, int64_t out_bstride) {
   const int b = blockIdx.y;
   const float ry = Hf > 1 ? (float)(h - 1) / (float)(Hf - 1) : 0.f, rx = Wf > 1 ? (float)(w - 1) / (float)(Wf - 1) : 0.f;
   const int64_t total = (int64_t)Ho * Wo;
@@ -115,7 +115,7 @@ logits_readout_kernel(const float* __restrict__ in, float* __restrict__ out, int
     const float* p11 = in + (((int64_t)b * h + y1) * w + x1) * cs;
     for (int c = 0; c < ncls; ++c) {
       const float v = (1.f - ly) * ((1.f - lx) * __ldg(p00 + c) + lx * __ldg(p01 + c)) + ly * ((1.f - lx) * __ldg(p10 + c) + lx * __ldg(p11 + c));
-      out[(((int64_t)b * ncls + c) * Ho + y) * Wo + x] = scale * v;
+      out[(int64_t)b * out_bstride + ((int64_t)c * Ho + y) * Wo + x] = scale * v;
     }
   }
 }
@@ -156,12 +156,14 @@ extern "C" int vt_resize_nearest_nhwc_f32(const float* in, float* out, int B, in
 }
 
 extern "C" int vt_logits_readout_f32(const float* in, float* out, int B, int h, int w, int c_stride, int n_classes, int Hf, int Wf,
-                                     int Ho, int Wo, int step, float scale, void* stream) {
+                                     int Ho, int Wo, int step, float scale, int64_t out_bstride, void* stream) {
+  if (out_bstride == 0) out_bstride = (int64_t)n_classes * Ho * Wo;
+  VT_CHECK(out_bstride >= (int64_t)n_classes * Ho * Wo, "logits_readout: out_bstride smaller than one sample");
   VT_CHECK(in && out && B >= 1 && B <= 65535 && h >= 1 && w >= 1 && n_classes >= 1 && c_stride >= n_classes, "logits_readout: bad args");
   VT_CHECK(step >= 1 && Ho >= 1 && Wo >= 1 && (int64_t)(Ho - 1) * step < Hf && (int64_t)(Wo - 1) * step < Wf,
            "logits_readout: the sampled pixels must lie inside the (Hf, Wf) grid");
   logits_readout_kernel<<<dim3(grid1((int64_t)Ho * Wo, 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(in, out, h, w, c_stride, n_classes,
-                                                                                                          Hf, Wf, Ho, Wo, step, scale);
+                                                                                                          Hf, Wf, Ho, Wo, step, scale, out_bstride);
   VT_LAUNCH_CHECK();
   return 0;
 }

@@ -21,8 +21,8 @@ class Linear(nn.Module):
         nn.init.uniform_(self.bias, -bound, bound)
         self.act = act
 
-    def forward(self, input):
-        return ops.linear(input, self.weight, self.bias, 1.0, 1.0, self.act)
+    def forward(self, input, act=None):
+        return ops.linear(input, self.weight, self.bias, 1.0, 1.0, self.act if act is None else act)
 
 
 class AdaptiveInstanceNorm(nn.Module):

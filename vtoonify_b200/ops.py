@@ -207,14 +207,17 @@ def _pad32(c: int) -> int:
 
 
 def prep_weights(W: torch.Tensor, style: Optional[torch.Tensor] = None, scale: float = 1.0, demodulate: bool = False,
-                 cin_pad: Optional[int] = None, round_tf32: Optional[bool] = None) -> torch.Tensor:
+                 cin_pad: Optional[int] = None, round_tf32: Optional[bool] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``W`` [Cout,Cin,kh,kw] (+ optional per-sample ``style`` [B,Cin]) -> conv-kernel layout
     ``[wB, kh*kw, Cout, cin_pad]`` = (scale*W)*style*demod (model/stylegan/model.py:259-267)."""
     _req_cuda(W, style)
     Cout, Cin, kh, kw = W.shape
     cin_pad = _pad32(Cin) if cin_pad is None else cin_pad
     wB = 1 if style is None else style.shape[0]
-    out = torch.empty((wB, kh * kw, Cout, cin_pad), device=W.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((wB, kh * kw, Cout, cin_pad), device=W.device, dtype=torch.float32)
+    elif tuple(out.shape) != (wB, kh * kw, Cout, cin_pad) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise _lib.VtError("prep_weights: bad out tensor")
     check(_lib.load().vt_modulate_weights_f32(W.contiguous().data_ptr(), _ptr(None if style is None else style.contiguous()),
                                               out.data_ptr(), wB, Cout, Cin, kh, kw, cin_pad, float(scale),
                                               int(demodulate), _round_flag() if round_tf32 is None else int(round_tf32),
@@ -593,9 +596,15 @@ def bilinear_add(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def axpby(a: torch.Tensor, b: Optional[torch.Tensor], sa: float, sb: float = 0.0, round_tf32: Optional[bool] = None) -> torch.Tensor:
-    _req_cuda(a, b)
-    out = torch.empty_like(a)
+def axpby(a: torch.Tensor, b: Optional[torch.Tensor], sa: float, sb: float = 0.0, round_tf32: Optional[bool] = None,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(a, b, out)
+    if not a.is_contiguous() or (b is not None and not b.is_contiguous()):
+        a, b = a.contiguous(), (None if b is None else b.contiguous())
+    if out is None:
+        out = torch.empty_like(a)
+    elif out.numel() != a.numel() or not out.is_contiguous():
+        raise _lib.VtError("axpby: out must be contiguous with as many elements as a")
     rt = _round_flag() if round_tf32 is None else int(round_tf32)
     check(_lib.load().vt_axpby_f32(a.data_ptr(), _ptr(b), out.data_ptr(), a.numel(), sa, sb, rt, _stream()))
     return out
@@ -659,13 +668,18 @@ def resize_nearest(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
     return out
 
 
-def logits_readout(logits: torch.Tensor, n_classes: int, Hf: int, Wf: int, step: int = 1, scale: float = 1.0) -> torch.Tensor:
+def logits_readout(logits: torch.Tensor, n_classes: int, Hf: int, Wf: int, step: int = 1, scale: float = 1.0,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """NHWC logits ``[B,h,w,Cs]`` -> planar ``[B,n_classes,ceil(Hf/step),ceil(Wf/step)]``: every ``step``-th pixel of the
-    ``align_corners=True`` bilinear up-sampling to ``(Hf, Wf)``."""
+    ``align_corners=True`` bilinear up-sampling to ``(Hf, Wf)``.  ``out``: optional channel slice ``t[:, c0:c0+n_classes]`` of a
+    contiguous planar tensor (written in place)."""
     _req_cuda(logits)
     B, h, w, Cs = logits.shape
     Ho, Wo = (Hf + step - 1) // step, (Wf + step - 1) // step
-    out = torch.empty((B, n_classes, Ho, Wo), device=logits.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((B, n_classes, Ho, Wo), device=logits.device, dtype=torch.float32)
+    elif tuple(out.shape) != (B, n_classes, Ho, Wo) or out.dtype != torch.float32 or out.stride()[1:] != (Ho * Wo, Wo, 1):
+        raise _lib.VtError("logits_readout: out must be a [B,n_classes,Ho,Wo] channel slice of a contiguous planar tensor")
     check(_lib.load().vt_logits_readout_f32(logits.contiguous().data_ptr(), out.data_ptr(), B, h, w, Cs, n_classes, Hf, Wf, Ho, Wo,
-                                            step, float(scale), _stream()))
+                                            step, float(scale), out.stride(0), _stream()))
     return out

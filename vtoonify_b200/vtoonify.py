@@ -56,7 +56,7 @@ class Conv2d(nn.Module):
         B, H, W, Cs = x.shape
         k = self.kernel_size
         npl = 0 if planar is None else planar.shape[1]
-        key = (self.weight.data_ptr(), self.weight._version)
+        key = (self.weight.data_ptr(), self.weight._version, npl)
         if getattr(self, "_split_key", None) != key:
             wt = self.weight.detach()
             self._w_nhwc_part = wt[:, npl:].contiguous()
@@ -83,7 +83,10 @@ class Conv2d(nn.Module):
         C = input.shape[1]
         x = ops.to_nhwc(input, ops._pad32(C) if C % 32 else None)
         if self.weight.shape[0] <= 4:
-            return self.forward_smalln(x)
+            if self.stride == 1 and 2 * self.padding == self.kernel_size - 1:
+                return self.forward_smalln(x)            # planar head: 'same' geometry only
+            from .op import conv2d_gradfix               # any other geometry: generic entry point (FFMA kernel)
+            return conv2d_gradfix.conv2d(input, self.weight, self.bias, stride=self.stride, padding=self.padding)
         return ops.nhwc_as_nchw_view(self.forward_nhwc(x))
 
 
@@ -139,12 +142,14 @@ class Fusion(nn.Module):
         self.conv = Conv2d(in_channels + skip_channels, out_channels, 3, 1, 1, bias=True)
         self.norm = AdaptiveInstanceNorm(in_channels + skip_channels, 128)
         self.conv2 = Conv2d(in_channels + skip_channels, 1, 3, 1, 1, bias=True)
-        self.linear = nn.Sequential(Linear(1, 64, act=2), LeakyReLU(0.2), Linear(64, 128, act=2), LeakyReLU(0.2))
+        # same indices / keys as the reference's Sequential(Linear, LeakyReLU, Linear, LeakyReLU); calling ``self.linear(x)``
+        # applies each LeakyReLU once, the fast path below fuses them into the Linear launches (act=2)
+        self.linear = nn.Sequential(Linear(1, 64), LeakyReLU(0.2), Linear(64, 128), LeakyReLU(0.2))
 
     def forward_nhwc(self, f_G, f_E, d_s=1):
         B = f_G.shape[0]
         label = torch.full((B, 1), float(d_s), device=f_G.device, dtype=torch.float32)
-        label = self.linear[2](self.linear[0](label))           # LeakyReLUs are fused into the Linears
+        label = self.linear[2](self.linear[0](label, act=2), act=2)   # LeakyReLU(0.2) fused into the Linear launches
         # AdaIN(cat(f_G, |f_G - f_E|)) is never materialised: plane statistics in one pass over (f_G, f_E), the affine
         # folded into per-sample mask-conv weights, and the mask conv reads f_G / f_E directly (virtual concat)
         stats = ops.instnorm_stats(f_G, f_E)

@@ -72,3 +72,50 @@ def test_aux_paths(golden, model):
     y2 = m(xa, sa, d_s=0.5)
     y0 = m(xa[:1], sa[:1], d_s=0.5)
     assert (y2[:1] - y0).abs().max().item() <= 1e-5
+
+
+def test_style_cache(golden, model):
+    """Per-style caching (one video = one style): identical results with and without cache hits, for shared (expanded or
+    repeated) and per-sample styles; in-place edits of the style tensor and reloaded weights invalidate the cache."""
+    from vtoonify_b200 import _lib
+    from vtoonify_b200.weights import det_state_dict
+    tag, m = model
+    g = golden(f"vtoonify_{tag}")
+    x, style = T(g["a_x"]).cuda(), T(g["a_style"]).cuda()          # B = 2, both rows carry the same code
+    assert torch.equal(style[0], style[1])
+    y_first = m(x, style, d_s=0.5)
+    n0 = _lib.launch_count()
+    y_hit = m(x, style, d_s=0.5)
+    n_hit = _lib.launch_count() - n0
+    assert torch.equal(y_first, y_hit)
+    s_exp = style[:1].expand(2, -1, -1)                              # the frame loop's stride-0 form: no device comparison needed
+    n0 = _lib.launch_count()
+    y_exp = m(x, s_exp, d_s=0.5)
+    n_miss = _lib.launch_count() - n0
+    assert torch.equal(y_first, y_exp)
+    assert n_hit < n_miss, f"a cache hit must launch fewer kernels ({n_hit} vs {n_miss})"
+    # per-sample styles: row 1 differs -> per-sample weights; each row equals its own single-sample run
+    s2 = style.clone()
+    s2[1] = s2[1] * 0.5 + 0.1
+    y2 = m(x, s2, d_s=0.5)
+    assert (y2[0:1] - m(x[0:1], s2[0:1], d_s=0.5)).abs().max().item() <= 1e-5
+    assert (y2[1:2] - m(x[1:2], s2[1:2], d_s=0.5)).abs().max().item() <= 1e-5
+    assert (y2[1] - y_first[1]).abs().max().item() > 1e-3
+    # in-place edit of a cached style tensor (version bump) must not serve stale weights
+    s3 = style.clone()
+    ya = m(x, s3, d_s=0.5)
+    s3.mul_(0.5)
+    yb = m(x, s3, d_s=0.5)
+    assert (ya - yb).abs().max().item() > 1e-3
+    assert torch.equal(yb, m(x, s3.clone(), d_s=0.5))
+    # a different d_s with the same style object
+    yd = m(x, style, d_s=0.25) if tag == "d" else None
+    if yd is not None:
+        assert (yd - y_first).abs().max().item() > 1e-4
+    # reloading (different) weights invalidates everything
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m.load_state_dict({k: v.cuda() for k, v in det_state_dict(m, seed=1).items()}, strict=True)
+    y_new = m(x, style, d_s=0.5)
+    assert (y_new - y_first).abs().max().item() > 1e-3
+    m.load_state_dict(sd0, strict=True)
+    assert torch.equal(m(x, style, d_s=0.5), y_first)

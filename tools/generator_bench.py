@@ -34,7 +34,7 @@ with torch.no_grad():
     ops.set_tc_profile(None)
     ms = e0.elapsed_time(e1) / steps
     per = {}
-    for a, b, f, nb, label in prof:
+    for a, b, f, nb, label, *_ in prof:
         d = per.setdefault(label, [0.0, 0.0, 0]); d[0] += a.elapsed_time(b); d[1] += f; d[2] += 1
     tc_ms = sum(v[0] for v in per.values()) / steps
     tc_fl = sum(v[1] for v in per.values()) / steps

@@ -34,14 +34,22 @@ class AdaptiveInstanceNorm(nn.Module):
         self.style.bias.data[:fin] = 1
         self.style.bias.data[fin:] = 0
 
+    def gamma_beta(self, style, B):
+        """[B, 2C] rows (gamma | beta) = Linear(style); style-only, so computed once per style inside a style scope
+        (a shared [1, D] style is broadcast to the batch)"""
+        def make():
+            gb = self.style(style)
+            return gb if gb.shape[0] == B else gb.expand(B, -1).contiguous()
+        return ops.style_cached(self, "gb", make, extra=(B, self.style.weight._version))
+
     def forward_nhwc(self, x, style, x2=None):
-        gb = self.style(style)
+        gb = self.gamma_beta(style, x.shape[0])
         stats = ops.instnorm_stats(x, x2)
         return ops.adain_apply(x, stats, gb, x2)
 
     def affine(self, x, style):
         """The same AdaIN as a [B, C, 2] (scale, shift) table for a convolution that applies it to its input on the fly."""
-        return ops.adain_affine(ops.instnorm_stats(x), self.style(style))
+        return ops.adain_affine(ops.instnorm_stats(x), self.gamma_beta(style, x.shape[0]))
 
     def forward(self, input, style):
         return ops.nhwc_as_nchw_view(self.forward_nhwc(ops.to_nhwc(input), style))
@@ -74,7 +82,7 @@ class AdaResBlock(nn.Module):
         return ops.nhwc_as_nchw_view(self.forward_nhwc(ops.to_nhwc(x), s, w))
 
 
-class DualStyleGAN(nn.Module):
+class DualStyleGAN(ops.WeightsEpochMixin, nn.Module):
     """model/dualstylegan.py:47-76 constructor (parameters / keys); VToonify only uses ``.style``, ``.res[7:]``
     and ``.generator`` at inference (model/vtoonify.py:214-224, 279-283)."""
 

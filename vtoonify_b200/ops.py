@@ -63,7 +63,7 @@ def get_option(name: str):
 
 
 # Optional per-launch timing of the tensor-core convolution (bench.py's roofline leg): when set to a list, every
-# vt_conv2d_tc_tf32 launch appends (start_event, end_event, algorithmic_flops, algorithmic_bytes, label).
+# vt_conv2d_tc_tf32 launch appends (start_event, end_event, algorithmic_flops, algorithmic_bytes, label, issued_mma_flops).
 _tc_profile = None
 
 
@@ -71,6 +71,87 @@ def set_tc_profile(sink):
     global _tc_profile
     old, _tc_profile = _tc_profile, sink
     return old
+
+
+# ----------------------------------------------------------------------------------------------
+# per-style caching: within one video every frame batch carries the same style code
+# (style_transfer.py:138-150, 176), so everything that depends on the style only -- the W+ transforms, the 15 modulation
+# linears, the modulated / demodulated / folded / split weights, the AdaIN gamma|beta rows -- is computed once per style.
+# A *scope* names the style by a token; modules memoise their style-only tensors per token (one entry per site, replaced when
+# the token changes).  Tokens are identity based (same tensor object, same version => same content), never content hashed.
+# ----------------------------------------------------------------------------------------------
+import itertools as _itertools
+
+_token_counter = _itertools.count(1)
+_scope_stack = []
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """invalidate every style token (called when a model's parameters are (re)loaded or moved)"""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+class WeightsEpochMixin:
+    """nn.Module mixin: ``load_state_dict`` / ``.to()`` / ``.cuda()`` invalidate the per-style caches"""
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        bump_weights_epoch()
+        return r
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        bump_weights_epoch()
+        return r
+
+
+class style_scope:
+    """``with ops.style_scope(token):`` — modules called inside memoise style-only tensors under ``token`` (None: no caching)."""
+
+    def __init__(self, token):
+        self.token = token
+
+    def __enter__(self):
+        _scope_stack.append(self.token)
+        return self
+
+    def __exit__(self, *exc):
+        _scope_stack.pop()
+        return False
+
+
+def style_token(owner, style: torch.Tensor, extra=()):
+    """-> (token, shared): ``token`` is stable while the caller keeps passing the same tensor object (unmodified) and ``extra``;
+    ``shared`` says that all batch rows of ``style`` are equal (one video, one style): an expanded (stride-0) tensor is
+    recognised for free, a materialised ``repeat`` by one device comparison when the object is first seen."""
+    st = owner.__dict__.get("_vt_style_state")
+    key = (style._version, tuple(style.shape), tuple(style.stride()), style.data_ptr(), tuple(extra), _precision, _weights_epoch)
+    if st is not None and st[0] is style and st[1] == key:
+        return st[2], st[3]
+    if style.shape[0] == 1 or style.stride(0) == 0:
+        shared = True
+    else:
+        shared = bool((style == style[:1]).all().item())       # one synchronising check per new style object
+    tok = next(_token_counter)
+    owner.__dict__["_vt_style_state"] = (style, key, tok, shared)
+    return tok, shared
+
+
+def style_cached(owner, name: str, fn, extra=None):
+    """memoise ``fn()`` on ``owner`` under the current style scope (recomputed when the token / ``extra`` / precision change)"""
+    tok = _scope_stack[-1] if _scope_stack else None
+    if tok is None:
+        return fn()
+    key = (tok, extra, _precision)
+    cache = owner.__dict__.setdefault("_vt_style_cache", {})
+    hit = cache.get(name)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = fn()
+    cache[name] = (key, val)
+    return val
 
 
 def _round_flag() -> int:
@@ -346,7 +427,10 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
             e0.record()
             check(lib.vt_conv2d_tc_tf32(d, _stream()))
             e1.record()
-            _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout}{'x4up' if d.n_phase > 1 else ''} k{len(taps)} s{stride} {H}x{W}"))
+            # MMA flops actually issued: 3 bf16 products per algorithmic product in the split-operand mode, and the folded
+            # up-convolution evaluates all 4 output phases with full 3x3 support (4x the transposed conv's algorithmic MACs)
+            issued = flops * (3.0 if prec == "bf16x3" else 1.0) * (4.0 if d.n_phase == 4 else 1.0)
+            _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout}{'x4up' if d.n_phase > 1 else ''} k{len(taps)} s{stride} {H}x{W}", issued))
         else:
             check(lib.vt_conv2d_tc_tf32(d, _stream()))
     else:

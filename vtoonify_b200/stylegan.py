@@ -188,11 +188,19 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def modulated_weights(self, style, cin_pad, externalweight=None, round_tf32=None):
-        """[B, k*k, Cout, cin_pad] = scale * (W [+ ext]) * s[b] * demod[b]  (model.py:259-267)."""
-        s = self.modulation(style)
-        W = self.weight[0] if externalweight is None else (self.weight + externalweight)[0]
-        return ops.prep_weights(W.detach(), s, self.scale, self.demodulate, cin_pad, round_tf32=round_tf32)
+    def modulated_weights(self, style, cin_pad, externalweight=None, round_tf32=None, folded=False):
+        """[B, k*k, Cout, cin_pad] = scale * (W [+ ext]) * s[b] * demod[b]  (model.py:259-267); ``folded``: the up-conv's
+        [B, 9, 4*Cout, cin_pad] phase kernels (Blur o conv_transpose).  Inside a style scope the result (and its bf16 split,
+        which is attached to the tensor) is computed once per style."""
+        def make():
+            s = self.modulation(style)
+            W = self.weight[0] if externalweight is None else (self.weight + externalweight)[0]
+            w = ops.prep_weights(W.detach(), s, self.scale, self.demodulate, cin_pad, round_tf32=round_tf32)
+            return ops.fold_upconv_weights(w, self.blur.kernel) if folded else w
+        if externalweight is not None:
+            return make()
+        return ops.style_cached(self, "w", make, extra=(cin_pad, round_tf32, folded, self.weight._version, self.weight.data_ptr(),
+                                                            self.modulation.weight._version, self.modulation.bias._version))
 
     def forward_nhwc(self, x, style, externalweight=None, bias=None, noise=None, noise_w=None, act=False,
                      slope=0.2, gain=ops.SQRT2, rgb=None):
@@ -206,8 +214,7 @@ class ModulatedConv2d(nn.Module):
                 raise NotImplementedError("upsampling ModulatedConv2d is 3x3 in StyleGAN2")
             if tuple(self.blur.kernel.shape) == (4, 4) and tuple(self.blur.pad) == (1, 1) and ops.use_folded_upconv(self.in_channel):
                 # Blur o conv_transpose folded into 4 phase-specific 3x3 kernels: one launch, no intermediate tensor
-                w9 = self.modulated_weights(style, Cs, externalweight, round_tf32=False)
-                wf = ops.fold_upconv_weights(w9, self.blur.kernel)
+                wf = self.modulated_weights(style, Cs, externalweight, round_tf32=False, folded=True)
                 return ops.conv_up2_folded_nhwc(x, wf, bias=bias, noise=noise, noise_w=noise_w, act=a, slope=slope, gain=gain)
             w = self.modulated_weights(style, Cs, externalweight)
             t = ops.conv_transpose2d_s2_k3_nhwc(x, w)
@@ -343,7 +350,7 @@ class ToRGB(nn.Module):
         return self.forward_nhwc(x, style, skip, externalweight)
 
 
-class Generator(nn.Module):
+class Generator(ops.WeightsEpochMixin, nn.Module):
     """model/stylegan/model.py:395-590 — same constructor, attributes and ``forward`` keyword interface."""
 
     def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01):
@@ -421,7 +428,14 @@ class Generator(nn.Module):
         if truncation < 1:
             styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
         latent = self._latent(styles, inject_index)
+        # per-latent caching of the modulated weights: valid while the caller passes the same (unmodified) tensor object again
+        # and nothing else shapes the latent (single style input, no truncation / mixing)
+        cacheable = len(styles) == 1 and input_is_latent and truncation >= 1 and latent is styles[0]
+        token = ops.style_token(self, latent)[0] if cacheable else None
+        with ops.style_scope(token):
+            return self._synthesis(latent, noise, return_latents, return_feature_ind)
 
+    def _synthesis(self, latent, noise, return_latents, return_feature_ind):
         out = ops.to_nhwc(self.input(latent))
         out = self.conv1.forward_nhwc(out, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1.forward_nhwc(out, latent[:, 1])

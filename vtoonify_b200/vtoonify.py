@@ -148,12 +148,15 @@ class Fusion(nn.Module):
 
     def forward_nhwc(self, f_G, f_E, d_s=1):
         B = f_G.shape[0]
-        label = torch.full((B, 1), float(d_s), device=f_G.device, dtype=torch.float32)
-        label = self.linear[2](self.linear[0](label, act=2), act=2)   # LeakyReLU(0.2) fused into the Linear launches
+
+        def make_gb():   # depends on d_s only: once per (style, d_s) scope
+            label = torch.full((B, 1), float(d_s), device=f_G.device, dtype=torch.float32)
+            label = self.linear[2](self.linear[0](label, act=2), act=2)   # LeakyReLU(0.2) fused into the Linear launches
+            return self.norm.style(label)
+        gb = ops.style_cached(self, "gb", make_gb, extra=(B, float(d_s)))
         # AdaIN(cat(f_G, |f_G - f_E|)) is never materialised: plane statistics in one pass over (f_G, f_E), the affine
         # folded into per-sample mask-conv weights, and the mask conv reads f_G / f_E directly (virtual concat)
         stats = ops.instnorm_stats(f_G, f_E)
-        gb = self.norm.style(label)
         C2 = 2 * f_G.shape[3]
         w_plain = self.conv2._wp.get(self.conv2.weight, 1.0, C2, round_tf32=False)          # [1, 9, 1, 2C]
         w_fold, k_fold = ops.affine_fold_weights(w_plain, stats, gb)
@@ -174,7 +177,7 @@ class Fusion(nn.Module):
         return ops.nhwc_as_nchw_view(f_out), m_E
 
 
-class VToonify(nn.Module):
+class VToonify(ops.WeightsEpochMixin, nn.Module):
     """model/vtoonify.py:130-286"""
 
     def __init__(self, in_size=256, out_size=1024, img_channels=3, style_channels=512, num_mlps=8,
@@ -242,8 +245,15 @@ class VToonify(nn.Module):
         return adastyles, resstyles
 
     def forward(self, x, style, d_s=None, return_mask=False, return_feat=False):
+        # One video = one style (style_transfer.py:138-150, 176): everything that depends on the style alone is computed once
+        # per style tensor and, when all batch rows carry the same code, as a single shared row (per-sample weights wB = 1).
+        token, shared = ops.style_token(self, style, (None if d_s is None else float(d_s),))
+        with ops.style_scope(token):
+            return self._forward(x, style[:1] if shared else style, d_s, return_mask, return_feat)
+
+    def _forward(self, x, style, d_s, return_mask, return_feat):
         D = self.backbone == 'dualstylegan'
-        adastyles, resstyles = self._styles(style)
+        adastyles, resstyles = ops.style_cached(self, "styles", lambda: self._styles(style))
 
         # encoder: downsampling conv blocks, then the res blocks (interleaved with dilated ModRes for D)
         feat = ops.to_nhwc(x, ops._pad32(x.shape[1]))

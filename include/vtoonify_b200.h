@@ -93,6 +93,10 @@ int vt_fold_upconv_weights_f32(const float* w, const float* blur, float* out, in
  * nstack_rows > 0 (N-stacked form, rows % nstack_rows == 0): out has 2*rows rows; each group of nstack_rows input rows
  * becomes nstack_rows rows [hi|hi] followed by nstack_rows rows [lo|lo]. */
 int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, int C, int nstack_rows, void* stream);
+/* The same split with fp16 halves (11 + 11 mantissa bits): out = [half(w*scale) x 32 | half(w*scale - hi) x 32] per 32-channel chunk.
+ * `scale` is a power of two that keeps the low halves out of fp16's subnormal range (undone by the consumer: vt_conv2d_rs acc_scale);
+ * |w * scale| must stay below 65504. */
+int vt_split_weights_f16x3(const float* w, void* out, int64_t rows, int C, float scale, void* stream);
 
 /* ---- convolution descriptor (NHWC activations) -------------------------------------------- */
 #define VT_MAX_TAPS 36     /* 9 taps x up to 4 output phases (folded up-conv) */
@@ -167,7 +171,15 @@ int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream);
  * Cout % 16 == 0, 16B-aligned views. */
 int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream);
 int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 accepts the descriptor */
-/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","tc_direct_store","smalln_is","fir4","upfirdn_tiled"};
+/* Row-strip tensor-core kernel for the full-resolution 3x3 / stride 1 / padding 1 layers with Cin, Cout in {32, 64} (StyledConv conv2 of
+ * the last generator levels, model/stylegan/model.py:298-304 + 364-392): the three vertical taps are stacked along the GEMM N dimension
+ * and the partial sums of an output row are accumulated across input rows inside TMEM.  Same descriptor; `weight_bf16x3` must hold the
+ * row-strip weight layout [wB][Cin/32][dx = -1,0,1][3*Cout rows: (dy = +1, 0, -1) x Cout][hi(32) | lo(32) 16-bit] and
+ * `bf16x3_nstack` names the split format (2: bf16, 3: fp16).  Epilogue: v = acc * acc_scale + bias + noise_w * noise -> activation
+ * (-> fused ToRGB tail).  Dense NHWC output only. */
+int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream);
+int vt_conv2d_rs_supported(const vt_conv_desc* d);
+/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","tc_direct_store","smalln_is","fir4","upfirdn_tiled","rs_cg","rs_rows"};
  * returns the previous value (-1 for an unknown key) */
 int vt_set_option(const char* key, int value);
 /* tuning only: device buffer of 148*16 uint64 that conv_tc fills with per-role wait-cycle counters (NULL disables) */

@@ -222,7 +222,7 @@ def vtoonify_forward(sd, x, style, d_s=None, backbone="dualstylegan", in_size=25
             f_E = feats[fi]
             if D:
                 fp = f"fusion_out.{fi}."
-                label = torch.zeros(out.shape[0], 1) + d_s
+                label = torch.zeros(out.shape[0], 1, device=out.device) + d_s
                 label = F.leaky_relu(F.linear(label, sd[fp + "linear.0.weight"], sd[fp + "linear.0.bias"]), 0.2)
                 label = F.leaky_relu(F.linear(label, sd[fp + "linear.2.weight"], sd[fp + "linear.2.bias"]), 0.2)
                 cat = torch.cat([out, (out - f_E).abs()], dim=1)

@@ -73,9 +73,12 @@ SYMBOLS = {
     "vt_modulate_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
     "vt_fold_upconv_weights_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vt_split_weights_bf16x3": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
+    "vt_split_weights_f16x3": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "vt_conv2d_direct_f32": (c_int, [POINTER(ConvDesc), _P]),
     "vt_conv2d_tc_tf32": (c_int, [POINTER(ConvDesc), _P]),
     "vt_conv2d_tc_supported": (c_int, [POINTER(ConvDesc)]),
+    "vt_conv2d_rs": (c_int, [POINTER(ConvDesc), c_float, _P]),
+    "vt_conv2d_rs_supported": (c_int, [POINTER(ConvDesc)]),
     "vt_set_option": (c_int, [c_char_p, c_int]),
     "vt_set_debug_buffer": (c_int, [_P]),
     "vt_smalln_conv_f32": (c_int, [POINTER(SmallNDesc), _P]),

@@ -616,12 +616,14 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
   }
 }
 
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-PFN_encodeTiled get_encode() {
+static PFN_encodeTiled get_encode() {
   static PFN_encodeTiled fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -635,8 +637,8 @@ PFN_encodeTiled get_encode() {
 }
 
 // 4-D fp32 tensor map, SWIZZLE_128B, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..3.
-int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3], const uint32_t box[4],
-              const char* what, bool bf16 = false) {
+int vt_tc_make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3], const uint32_t box[4],
+                    const char* what, bool bf16) {
   PFN_encodeTiled enc = get_encode();
   VT_CHECK(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -652,6 +654,11 @@ int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const ui
   VT_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
   return 0;
 }
+
+
+namespace {
+inline int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3], const uint32_t box[4],
+                     const char* what, bool bf16 = false) { return vt_tc_make_map4(m, base, dims, strides_b, box, what, bf16); }
 
 int g_tc_mode = 1;  // 0: one TMA box per tap; 1: one halo box per K chunk + row-shifted descriptors
 int g_tc_mt = 0;    // 0: automatic M-tiles per work item; 1/2/4: forced
@@ -692,7 +699,10 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
 
 }  // namespace
 
+int vt_rs_set_option(const char* key, int value, int* old);   // conv_rs.cu
+
 extern "C" int vt_set_option(const char* key, int value) {
+  { int old = 0; if (vt_rs_set_option(key, value, &old)) return old; }
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
@@ -706,7 +716,8 @@ extern "C" int vt_set_option(const char* key, int value) {
   return -1;
 }
 
-extern "C" int vt_set_debug_buffer(void* p) { g_tc_dbg = (unsigned long long*)p; return 0; }
+unsigned long long* g_tc_dbg_export = nullptr;   // the same buffer, visible to conv_rs.cu
+extern "C" int vt_set_debug_buffer(void* p) { g_tc_dbg = (unsigned long long*)p; g_tc_dbg_export = g_tc_dbg; return 0; }
 
 extern "C" int vt_conv2d_tc_supported(const vt_conv_desc* d) {
   if (!d || d->struct_size != (int)sizeof(vt_conv_desc)) return 0;

@@ -9,6 +9,7 @@
 //                             With style == NULL it is the plain re-layout used for nn.Conv2d / EqualConv2d weights.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -231,6 +232,42 @@ extern "C" int vt_split_weights_bf16x3(const float* w, void* out, int64_t rows, 
   VT_CHECK(((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 15) == 0, "split_weights_bf16x3: pointers must be 16-byte aligned");
   const int64_t n_quads = rows * C / 4;
   split_bf16x3_kernel<<<(unsigned)vt_cdiv(n_quads, 256), 256, 0, (cudaStream_t)stream>>>(w, (uint2*)out, n_quads, C, nstack_rows);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- fp16 split of weight rows: out chunk = [half(w * scale) x 32 | half(w * scale - hi) x 32] ---------------------------------
+// fp16 keeps 11 + 11 mantissa bits (bf16: 8 + 8), i.e. the split represents w to 2^-22 as long as both halves stay in fp16's
+// normal range: `scale` (a power of two, undone by the consumer's acc_scale) lifts the small demodulated weights away from the
+// subnormals; |w * scale| must stay below 65504.
+__global__ void __launch_bounds__(256)
+split_f16x3_kernel(const float* __restrict__ w, uint2* __restrict__ out, int64_t n_quads, float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+  const float f[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+  unsigned short h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half hb = __float2half_rn(f[k]);
+    h[k] = __half_as_ushort(hb);
+    l[k] = __half_as_ushort(__float2half_rn(f[k] - __half2float(hb)));
+  }
+  const uint2 hq = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  const uint2 lq = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  const int64_t chunk = i >> 3;
+  const int q = (int)(i & 7);
+  uint2* base = out + chunk * 16;
+  base[q] = hq;
+  base[8 + q] = lq;
+}
+
+extern "C" int vt_split_weights_f16x3(const float* w, void* out, int64_t rows, int C, float scale, void* stream) {
+  VT_CHECK(w && out && rows >= 1 && C >= 32 && C % 32 == 0, "split_weights_f16x3: bad args (rows=%lld C=%d)", (long long)rows, C);
+  VT_CHECK(scale > 0.f, "split_weights_f16x3: scale must be positive");
+  VT_CHECK(((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 15) == 0, "split_weights_f16x3: pointers must be 16-byte aligned");
+  const int64_t n_quads = rows * C / 4;
+  split_f16x3_kernel<<<(unsigned)vt_cdiv(n_quads, 256), 256, 0, (cudaStream_t)stream>>>(w, (uint2*)out, n_quads, scale);
   VT_LAUNCH_CHECK();
   return 0;
 }

@@ -5,6 +5,11 @@
 #include <cuda.h>
 #include "common.cuh"
 
+// 4-D tensor map (fp32 or bf16/fp16-sized 2-byte elements), SWIZZLE_128B, zero OOB fill; dims / box innermost first, strides in
+// BYTES for dims 1..3 (defined in conv_tc.cu)
+int vt_tc_make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3], const uint32_t box[4],
+                    const char* what, bool bf16);
+
 namespace vt_tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

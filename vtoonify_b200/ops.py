@@ -42,7 +42,11 @@ def get_precision() -> str:
 # fold_upconv: True = always fold Blur o conv_transpose into one N = 4*Cout convolution; an int = only when Cin <= that value
 # (the folded form issues 4x the MMA work but has no intermediate tensor: measured faster for Cin <= 128, slower from Cin = 256 up:
 # tools/upconv_bench.py).  fuse_mask_mul: Fusion's f_E * m_E is applied inside the consumers instead of being materialised.
-_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False, "fuse_adain": True}
+# rs_conv: route 3x3 / stride 1 / padding 1 layers with Cin, Cout in {32, 64} and at least rs_min_width pixels per row to the
+# row-strip kernel (vertical taps stacked along N, cross-row accumulation in TMEM: conv_rs.cu); rs_fmt: its operand split
+# ("bf16" | "f16": fp16 halves carry 11 + 11 mantissa bits instead of 8 + 8, weights pre-scaled by 2^10).
+_options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False, "fuse_adain": True,
+            "rs_conv": True, "rs_min_width": 256, "rs_fmt": "bf16"}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 
@@ -407,6 +411,30 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                     raise _lib.VtError("conv2d_nhwc: src_affine must be a contiguous [B, C, 2] table")
                 d.src_affine[i] = af.data_ptr()
     lib = _lib.load()
+    if (prec == "bf16x3" and _options["rs_conv"] and W >= _options["rs_min_width"] and len(srcs) == 1 and phase_offs is None
+            and stride == 1 and len(taps) == 9 and res is None and slope_vec is None and src_scale is None and src_affine is None
+            and Cout in (32, 64) and int(d.src_c[0]) in (32, 64) and w_cs == int(d.src_c[0]) and alpha == 1.0
+            and act in (ACT_NONE, ACT_LRELU)):
+        # full-resolution small-channel 3x3 layer: the row-strip kernel (falls through when the descriptor is not eligible)
+        fmt = _options["rs_fmt"]
+        wrs, acc_scale = rs_weights(weight, fmt)
+        d.weight_bf16x3 = wrs.data_ptr()
+        d.bf16x3_nstack = 3 if fmt == "f16" else 2
+        if lib.vt_conv2d_rs_supported(d):
+            if _tc_profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cin = int(d.src_c[0])
+                flops = 2.0 * B * Ho * Wo * Cout * cin * 9
+                nbytes = 4.0 * (B * H * W * cin + B * Ho * Wo * Cout + weight.numel())
+                e0.record()
+                check(lib.vt_conv2d_rs(d, acc_scale, _stream()))
+                e1.record()
+                _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout} k9 s1 {H}x{W} [row-strip]", 3.0 * flops))
+            else:
+                check(lib.vt_conv2d_rs(d, acc_scale, _stream()))
+            return out if rgb is None else (out, rgb_out)
+        d.weight_bf16x3 = None
+        d.bf16x3_nstack = 0
     if prec == "bf16x3":
         d.weight_bf16x3 = weight.data_ptr()   # marks the mode for vt_conv2d_tc_supported; the split buffer is attached below
     use_tc = prec in ("tf32", "bf16x3") and lib.vt_conv2d_tc_supported(d)
@@ -455,6 +483,32 @@ def split_weights_bf16x3(weight: torch.Tensor, nstack: bool = False) -> torch.Te
     check(_lib.load().vt_split_weights_bf16x3(weight.data_ptr(), out.data_ptr(), rows, weight.shape[-1], nrows, _stream()))
     weight._vt_bf16x3 = (ver, weight.data_ptr(), out, nstack)
     return out
+
+
+def rs_weights(weight: torch.Tensor, fmt: str = "bf16"):
+    """``weight`` [wB, 9, Cout, Cin] (prep layout, tap = ky*3 + kx, Cin in {32, 64}) -> (buffer, acc_scale) for vt_conv2d_rs:
+    rows ordered [wB][Cin/32][kx][block = 2 - ky][Cout], each a 32-channel chunk split into 16-bit hi | lo halves.
+    Cached on the tensor object like :func:`split_weights_bf16x3`."""
+    ver = weight._version
+    cached = getattr(weight, "_vt_rs", None)
+    if cached is not None and cached[0] == ver and cached[1] == weight.data_ptr() and cached[2] == fmt:
+        return cached[3], cached[4]
+    wB, nine, Cout, Cin = weight.shape
+    if nine != 9 or Cin % 32 != 0 or not weight.is_contiguous():
+        raise _lib.VtError("rs_weights: needs contiguous [wB, 9, Cout, Cin] weights with Cin a multiple of 32")
+    KC = Cin // 32
+    w = weight.view(wB, 3, 3, Cout, KC, 32).flip(1).permute(0, 4, 2, 1, 3, 5).contiguous()   # [wB, KC, kx, 2-ky, Cout, 32]
+    rows = w.numel() // 32
+    out = torch.empty((rows, 32), device=weight.device, dtype=torch.float32)
+    if fmt == "f16":
+        scale = 1024.0
+        check(_lib.load().vt_split_weights_f16x3(w.data_ptr(), out.data_ptr(), rows, 32, scale, _stream()))
+        acc_scale = 1.0 / scale
+    else:
+        check(_lib.load().vt_split_weights_bf16x3(w.data_ptr(), out.data_ptr(), rows, 32, 0, _stream()))
+        acc_scale = 1.0
+    weight._vt_rs = (ver, weight.data_ptr(), fmt, out, acc_scale)
+    return out, acc_scale
 
 
 def affine_fusable(precision: Optional[str] = None) -> bool:

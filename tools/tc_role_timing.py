@@ -53,6 +53,34 @@ def up_case(B, Cin, Cout, H, W):
 ops.set_precision(sys.argv[1] if len(sys.argv) > 1 else ops.DEFAULT_PRECISION)
 print("precision", ops.get_precision())
 with torch.no_grad():
+    if len(sys.argv) > 2 and sys.argv[2] == "rs":
+        for rs in (False, True):
+            ops.set_option("rs_conv", rs)
+            print("row-strip kernel" if rs else "tap-by-tap kernel")
+            for fmt in (("bf16", "f16") if rs else ("bf16",)):
+                ops.set_option("rs_fmt", fmt)
+                conv_case(4, 32, 32, 2304, 4096)
+                conv_case(4, 32, 32, 2304, 4096, rgb=True)
+                conv_case(4, 64, 64, 1152, 2048)
+                conv_case(4, 64, 64, 1152, 2048, rgb=True)
+                conv_case(8, 32, 32, 1024, 1024, rgb=True)
+        ops.set_option("rs_fmt", "bf16")
+        for strict in (1, 0):
+            lib.vt_set_option(b"rs_strict", strict)
+            print("strict cluster-scope release" if strict else "plain remote arrive")
+            conv_case(4, 32, 32, 2304, 4096, rgb=True)
+            conv_case(4, 64, 64, 1152, 2048, rgb=True)
+        for cg in (1, 2):
+            lib.vt_set_option(b"rs_cg", cg)
+            print("rs_cg", cg)
+            conv_case(4, 32, 32, 2304, 4096, rgb=True)
+        lib.vt_set_option(b"rs_cg", 0)
+        for rows in (48, 96):
+            lib.vt_set_option(b"rs_rows", rows)
+            print("rows_per_strip", rows)
+            conv_case(4, 32, 32, 2304, 4096, rgb=True)
+        lib.vt_set_option(b"rs_rows", 0)
+        sys.exit(0)
     conv_case(4, 512, 512, 72, 128)
     conv_case(4, 256, 256, 288, 512)
     conv_case(4, 128, 128, 576, 1024)

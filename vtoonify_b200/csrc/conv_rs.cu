@@ -19,8 +19,10 @@
 // `rows_per_strip` rows and streams each input row once: TMA box (32 ch, 130 px, 1 row) with a 1-pixel halo, zero-filled outside
 // the image (= the conv's zero padding); dx = -1, 0, +1 are descriptor start addresses shifted by whole 128-byte rows.  The
 // weights of all 9 taps stay resident in shared memory for the whole launch (36 KB for 32->32).
-// Roles (10 warps): 0 TMA producer | 1 MMA issuer | 2,3,8,9 operand transform (fp32 -> [hi|lo] 16-bit split, in place) | 4-7 epilogue
-// (TMEM -> bias / noise / leaky-relu / fused ToRGB + skip up-sampling -> per-warp swizzled staging -> per-warp TMA store).
+// Roles (14 warps): 0 TMA producer | 1 MMA issuer | 2,3,12,13 operand transform (fp32 -> [hi|lo] 16-bit split, in place) |
+// 4-7 and 8-11: two epilogue groups that take finished rows alternately (TMEM -> bias / noise / leaky-relu / fused ToRGB + skip
+// up-sampling -> per-warp swizzled staging -> per-warp TMA store); the epilogue is a chain of latencies (barrier, TMEM, shared
+// memory constants, proxy fence), two rows in flight hide them.
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -35,10 +37,10 @@ namespace {
 constexpr int RS_PX = 128;                 // pixels per CTA row segment = MMA M per CTA
 constexpr int RS_BOX = RS_PX + 2;          // with the 1-pixel halo on both sides
 constexpr int RS_A_STAGE = 17 * 1024;      // 130 rows x 128 B, padded to the 1024-byte swizzle atom
-constexpr int RS_THREADS = 320;
+constexpr int RS_THREADS = 448;
 constexpr int RS_XFORM_WARPS = 4;
 constexpr int RS_MAX_SMEM = 227 * 1024;
-constexpr int RS_STAGING = 4 * 2 * 4096;   // per epilogue warp: two 32 px x 128 B buffers
+constexpr int RS_STAGING = 8 * 2 * 4096;   // per epilogue warp: two 32 px x 128 B buffers
 constexpr int RS_CONST_FLOATS = 64 + 3 * 64 + 4 + 16;   // bias | rgb_w[3][64] | rgb_bias (3, padded) | skip kernel
 
 struct RsArgs {
@@ -55,6 +57,7 @@ struct RsArgs {
   const float* rgb_w; const float* rgb_bias; const float* rgb_skip; const float* rgb_skip_kernel; float* rgb_out;
   int fmt;                 // operand split: 0 = bf16 hi/lo, 1 = fp16 hi/lo
   float acc_scale;         // accumulators are multiplied by this before the bias (undoes a power-of-two weight scale)
+  int strict_release;      // 1: cluster-scope release on the transform warps' remote arrive (A/B switch for tests)
   unsigned long long* dbg;
 };
 
@@ -67,6 +70,20 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
       "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
       ::"r"(taddr), "r"(z)
       : "memory");
+}
+// this warp's 32 lanes x 16 consecutive columns, added into acc[0..15]
+__device__ __forceinline__ void tmem_ld16_add(uint32_t taddr, float* acc) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -104,6 +121,8 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
   const int S = p.S, Cout = p.Cout, N = 3 * p.Cout;
   long long tw[4] = {0, 0, 0, 0};
   const long long t_begin = clock64();
+  const bool is_epi = warp >= 4 && warp < 12;
+  const bool is_xform = warp == 2 || warp == 3 || warp >= 12;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.in_map); tma_prefetch_desc(&p.w_map); tma_prefetch_desc(&p.out_map);
@@ -142,6 +161,10 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
     R = min(p.rows_per_strip, p.H - y0);
     x0 = xs * (RS_PX * CG) + (int)rank * RS_PX;
   };
+  // A strip of R output rows y0 .. y0+R-1 streams the R+2 input rows y0-1 .. y0+R (index i).  Input row i adds into the output
+  // rows k = i, i+1, i+2 where k counts from y0-2: rows k = 0, 1 and k = R+2, R+3 only ever hold incomplete sums (they belong to
+  // the neighbouring strips) and are just drained; k = 2 .. R+1 are produced.  Output row y lives in slot (y + 2) mod S, i.e.
+  // row k of the strip in slot (y0 + k) mod S.
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -183,10 +206,12 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
     const uint32_t idesc = p.fmt ? make_idesc_f16(RS_PX * CG, N) : make_idesc_bf16(RS_PX * CG, N);
     int a_st = 0; uint32_t a_par = 0, w_par = 0;
     int cur_wb = -1;
-    int g = 1;              // global input-row counter; input row g accumulates into output rows g-1, g, g+1
-    int slot_prev = 0;      // (g - 1) mod S
-    int slot_new = 2 % S;   // (g + 1) mod S
-    uint32_t lap_new = (uint32_t)(2 / S);   // (g + 1) / S
+    uint32_t acq = 0;       // bit q: parity of the number of times slot q has been handed to a new output row
+    auto acquire = [&](int q) {
+      // the slot's previous output row has been read and zeroed by both CTAs' epilogues (first use: a fresh barrier passes)
+      RS_TWAIT(2, mbar_wait(row_empty(q), ((acq >> q) & 1u) ^ 1u, 24));
+      acq ^= 1u << q;
+    };
     for (int strip = cta_i; strip < p.total_strips; strip += cta_n) {
       int b, y0, x0, R;
       strip_geom(strip, b, y0, x0, R);
@@ -194,11 +219,14 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
       if (wb != cur_wb) { RS_TWAIT(1, mbar_wait(w_full, w_par, 23)); w_par ^= 1; cur_wb = wb; }
       int next_wb = wb;
       if (strip + cta_n < p.total_strips && p.wB > 1) next_wb = (strip + cta_n) / strips_per_img;
+      int qs = y0 % S;      // slot of output row k = i (the first row of input i's window)
       for (int i = 0; i < R + 2; ++i) {
-        // the slot that becomes output row g+1 was output row g+1-S: drained (read + zeroed) by both epilogues
-        RS_TWAIT(2, mbar_wait(row_empty(slot_new), (lap_new & 1u) ^ 1u, 24));
+        int q1 = qs + 1; if (q1 >= S) q1 -= S;
+        int q2 = q1 + 1; if (q2 >= S) q2 -= S;
+        if (i == 0) { acquire(qs); acquire(q1); }
+        acquire(q2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(slot_prev * Cout);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(qs * Cout);   // physical window qs .. qs+2 (slots S, S+1 mirror 0, 1)
         for (int kc = 0; kc < p.KC; ++kc) {
           RS_TWAIT(0, mbar_wait(a_ready(a_st), a_par, 25));
           tc_fence_after();
@@ -231,21 +259,25 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
           __syncwarp();
           if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
         }
-        // output row g-1 has received its three contributions
-        if (elect_one()) { if (CG == 2) umma_commit_2sm(row_full(slot_prev)); else umma_commit(row_full(slot_prev)); }
+        // output row k = i has received its last contribution; after the last input row so have the two trailing rows
+        if (elect_one()) {
+          if (CG == 2) umma_commit_2sm(row_full(qs)); else umma_commit(row_full(qs));
+          if (i == R + 1) {
+            if (CG == 2) { umma_commit_2sm(row_full(q1)); umma_commit_2sm(row_full(q2)); }
+            else { umma_commit(row_full(q1)); umma_commit(row_full(q2)); }
+          }
+        }
         __syncwarp();
-        ++g;
-        if (++slot_prev == S) slot_prev = 0;
-        if (++slot_new == S) { slot_new = 0; ++lap_new; }
+        qs = q1;
       }
       if (next_wb != wb) {
         if (elect_one()) { if (CG == 2) umma_commit_2sm(w_empty); else umma_commit(w_empty); }
         __syncwarp();
       }
     }
-  } else if (warp == 2 || warp == 3 || warp >= 8) {
+  } else if (is_xform) {
     // ================= operand transform: fp32 rows -> [hi(32) | lo(32)] 16-bit rows, in place =================
-    const int t = (warp < 4 ? warp - 2 : warp - 6) * 32 + lane;   // 0 .. 127
+    const int t = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;   // 0 .. 127
     int a_st = 0; uint32_t a_par = 0;
     for (int strip = cta_i; strip < p.total_strips; strip += cta_n) {
       int b, y0, x0, R;
@@ -290,24 +322,30 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((m4 + 4) ^ ph) << 4)), "r"(lo[4 * m4]), "r"(lo[4 * m4 + 1]), "r"(lo[4 * m4 + 2]), "r"(lo[4 * m4 + 3]) : "memory");
           }
         }
+        // Every lane has made its own rows visible to the async proxy (the fence waits until the stores are performed in this
+        // SM's shared memory, which has a single copy), so a plain remote arrive is enough for the pair's issuing thread: a
+        // cluster-scope release (MEMBAR.ALL.GPU) costs ~2k cycles per stage and made this warp role the bottleneck (measured).
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { if (CG == 2) mbar_arrive_cta0_release(a_ready(a_st)); else mbar_arrive(a_ready(a_st)); }
+        if (lane == 0) { if (CG == 2) { if (p.strict_release) mbar_arrive_cta0_release(a_ready(a_st)); else mbar_arrive_cta0(a_ready(a_st)); } else mbar_arrive(a_ready(a_st)); }
         if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================= epilogue =================
-    const int q = warp - 4;
+  } else if (is_epi) {
+    // ================= epilogue: two groups of four warps take finished rows alternately =================
+    const int grp = (warp - 4) >> 2;             // 0: warps 4-7, 1: warps 8-11
+    const int q = (warp - 4) & 3;                // TMEM lane quadrant (== warp % 4)
     const int r = q * 32 + lane;                 // accumulator lane == pixel of the row segment
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t sbuf0 = st_base + (uint32_t)q * 8192u;
+    const uint32_t sbuf0 = st_base + (uint32_t)(warp - 4) * 8192u;
     const float nw = (p.noise && p.noise_w) ? *p.noise_w : 0.f;
     const int nchunks = Cout / 32;
     const int64_t HW = (int64_t)p.H * p.W;
     const int hs = p.H >> 1, ws = p.W >> 1;
+    const bool timed = p.dbg != nullptr && grp == 0;
     uint32_t n_store = 0;
-    int G = 0, slot = 0; uint32_t lap = 0;
+    uint32_t full_par = 0;   // bit q: parity of the number of finished rows slot q has delivered so far
+    uint32_t turn = 0;       // finished rows seen so far (both groups count all of them; a group works on those with its parity)
     int cur_wb = -1;
     for (int strip = cta_i; strip < p.total_strips; strip += cta_n) {
       int b, y0, x0, R;
@@ -317,8 +355,8 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
       const bool x_in = x < p.W;
       if (wb != cur_wb) {
         // epilogue constants of this sample -> shared memory (bias, ToRGB weights / bias, skip kernel)
-        named_bar_sync(1, 128);                  // nobody still reads the previous sample's constants
-        for (int i = r; i < RS_CONST_FLOATS; i += 128) {
+        named_bar_sync(1, 256);                  // nobody still reads the previous sample's constants
+        for (int i = grp * 128 + r; i < RS_CONST_FLOATS; i += 256) {
           float v = 0.f;
           if (i < 64) v = (p.bias && i < Cout) ? __ldg(p.bias + i) : 0.f;
           else if (i < 256) { const int c = (i - 64) / 64, n = (i - 64) % 64; v = (p.rgb_w && n < Cout) ? __ldg(p.rgb_w + ((int64_t)wb * 3 + c) * Cout + n) : 0.f; }
@@ -326,10 +364,11 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
           else v = p.rgb_skip ? __ldg(p.rgb_skip_kernel + (i - 260)) : 0.f;
           cst[i] = v;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         cur_wb = wb;
       }
-      // software pipeline: the global loads of the NEXT valid row (noise, skip pixels) are issued one row ahead
+      // software pipeline: the global loads of this group's NEXT produced row (noise, skip pixels) are issued one turn ahead,
+      // right after the proxy fence of the current row (a fence would otherwise wait for them)
       float nz_next = 0.f, sk_next[12];
 #pragma unroll
       for (int i = 0; i < 12; ++i) sk_next[i] = 0.f;
@@ -348,12 +387,19 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
           }
         }
       };
-      prefetch(y0);
-      // The k-th finished row of this strip (signalled after its k-th input row, y0 - 1 + k) is output row y0 - 2 + k: the first
-      // two (the neighbouring strip's territory, incomplete sums) are only drained, rows y0 .. y0 + R - 1 are produced.
-      for (int k = 0; k < R + 2; ++k) {
+      {   // this group's first produced row of the strip: k = 2 or 3
+        const int kf = 2 + (int)(((turn + 2u) & 1u) != (uint32_t)grp);
+        if (kf <= R + 1) prefetch(y0 - 2 + kf);
+      }
+      int slot = y0 % S;     // slot of row k = 0
+      for (int k = 0; k < R + 4; ++k, ++turn) {
+        const int cur = slot;
+        if (++slot == S) slot = 0;
+        const uint32_t par = (full_par >> cur) & 1u;
+        full_par ^= 1u << cur;                     // both groups track every row's barrier phase
+        if ((turn & 1u) != (uint32_t)grp) continue;
         const int y = y0 - 2 + k;
-        const bool valid = k >= 2;
+        const bool valid = k >= 2 && k <= R + 1;
         float nz = 0.f, sk[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) sk[i] = 0.f;
@@ -361,82 +407,79 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
           nz = nz_next;
 #pragma unroll
           for (int i = 0; i < 12; ++i) sk[i] = sk_next[i];
-          if (k + 1 < R + 2) prefetch(y + 1);
         }
-        RS_TWAIT(0, mbar_wait(row_full(slot), lap & 1u, 27));
+        if (timed) { const long long t__ = clock64(); mbar_wait(row_full(cur), par, 27); tw[0] += clock64() - t__; }
+        else mbar_wait(row_full(cur), par, 27);
+        const long long t_e0 = timed ? clock64() : 0;
         tc_fence_after();
-        float v[64];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < nchunks) {
-            const uint32_t col = (uint32_t)(slot * Cout + c * 32);
-            tmem_ld32(t_lane + col, v + 32 * c);
-            tmem_zero32(t_lane + col);
-            if (slot < 2) {   // rows 0 and 1 of a lap also collected partial sums in the mirror slots S, S+1
-              float m[32];
-              const uint32_t mcol = (uint32_t)((S + slot) * Cout + c * 32);
-              tmem_ld32(t_lane + mcol, m);
-              tmem_zero32(t_lane + mcol);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[32 * c + i] += m[i];
-            }
-          }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (CG == 2) mbar_arrive_cta0(row_empty(slot)); else mbar_arrive(row_empty(slot)); }
-        ++G;
-        if (++slot == S) { slot = 0; ++lap; }
-        if (!valid) continue;
-
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          float v[32];
+          const uint32_t col = (uint32_t)(cur * Cout + c * 32);
+          tmem_ld32(t_lane + col, v);
+          tmem_zero32(t_lane + col);
+          if (cur < 2) {   // rows in slots 0 and 1 also collected partial sums in the mirror slots S, S+1
+            const uint32_t mcol = (uint32_t)((S + cur) * Cout + c * 32);
+            tmem_ld16_add(t_lane + mcol, v);
+            tmem_ld16_add(t_lane + mcol + 16u, v + 16);
+            tmem_zero32(t_lane + mcol);
+          }
+          if (c == nchunks - 1) {
+            // the slot is clean again: hand it back to the MMA issuer before the math
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cta0(row_empty(cur)); else mbar_arrive(row_empty(cur)); }
+          }
+          if (!valid) continue;
+          const long long t_e1 = timed ? clock64() : 0;
+          if (timed) tw[1] += t_e1 - t_e0;
+          const float4* bp = reinterpret_cast<const float4*>(cst + 32 * c);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < nchunks) {
-            float* vv = v + 32 * c;
-            const float4* bp = reinterpret_cast<const float4*>(cst + 32 * c);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bq = bp[i];
+            v[4 * i + 0] = fmaf(v[4 * i + 0], p.acc_scale, bq.x + nz); v[4 * i + 1] = fmaf(v[4 * i + 1], p.acc_scale, bq.y + nz);
+            v[4 * i + 2] = fmaf(v[4 * i + 2], p.acc_scale, bq.z + nz); v[4 * i + 3] = fmaf(v[4 * i + 3], p.acc_scale, bq.w + nz);
+          }
+          if (p.act == VT_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = vt_lrelu(v[i], p.slope) * p.gain;
+          }
+          if (p.rgb_w) {
+            const float4* w0 = reinterpret_cast<const float4*>(cst + 64 + 32 * c);
+            const float4* w1 = reinterpret_cast<const float4*>(cst + 128 + 32 * c);
+            const float4* w2 = reinterpret_cast<const float4*>(cst + 192 + 32 * c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 bq = bp[i];
-              vv[4 * i + 0] = fmaf(vv[4 * i + 0], p.acc_scale, bq.x + nz); vv[4 * i + 1] = fmaf(vv[4 * i + 1], p.acc_scale, bq.y + nz);
-              vv[4 * i + 2] = fmaf(vv[4 * i + 2], p.acc_scale, bq.z + nz); vv[4 * i + 3] = fmaf(vv[4 * i + 3], p.acc_scale, bq.w + nz);
+              const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i];
+              rgb0 = fmaf(v[4 * i], a0.x, rgb0); rgb0 = fmaf(v[4 * i + 1], a0.y, rgb0); rgb0 = fmaf(v[4 * i + 2], a0.z, rgb0); rgb0 = fmaf(v[4 * i + 3], a0.w, rgb0);
+              rgb1 = fmaf(v[4 * i], a1.x, rgb1); rgb1 = fmaf(v[4 * i + 1], a1.y, rgb1); rgb1 = fmaf(v[4 * i + 2], a1.z, rgb1); rgb1 = fmaf(v[4 * i + 3], a1.w, rgb1);
+              rgb2 = fmaf(v[4 * i], a2.x, rgb2); rgb2 = fmaf(v[4 * i + 1], a2.y, rgb2); rgb2 = fmaf(v[4 * i + 2], a2.z, rgb2); rgb2 = fmaf(v[4 * i + 3], a2.w, rgb2);
             }
-            if (p.act == VT_ACT_LRELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) vv[i] = vt_lrelu(vv[i], p.slope) * p.gain;
-            }
-            if (p.rgb_w) {
-              const float4* w0 = reinterpret_cast<const float4*>(cst + 64 + 32 * c);
-              const float4* w1 = reinterpret_cast<const float4*>(cst + 128 + 32 * c);
-              const float4* w2 = reinterpret_cast<const float4*>(cst + 192 + 32 * c);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i];
-                rgb0 = fmaf(vv[4 * i], a0.x, rgb0); rgb0 = fmaf(vv[4 * i + 1], a0.y, rgb0); rgb0 = fmaf(vv[4 * i + 2], a0.z, rgb0); rgb0 = fmaf(vv[4 * i + 3], a0.w, rgb0);
-                rgb1 = fmaf(vv[4 * i], a1.x, rgb1); rgb1 = fmaf(vv[4 * i + 1], a1.y, rgb1); rgb1 = fmaf(vv[4 * i + 2], a1.z, rgb1); rgb1 = fmaf(vv[4 * i + 3], a1.w, rgb1);
-                rgb2 = fmaf(vv[4 * i], a2.x, rgb2); rgb2 = fmaf(vv[4 * i + 1], a2.y, rgb2); rgb2 = fmaf(vv[4 * i + 2], a2.z, rgb2); rgb2 = fmaf(vv[4 * i + 3], a2.w, rgb2);
-              }
-            }
-            // per-warp staging (32 pixels x 128 B, 128B-swizzled) + per-warp TMA store: no CTA-wide barrier in the epilogue
-            const uint32_t sbuf = sbuf0 + (n_store & 1u) * 4096u;
-            if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer two stores ago has read it
-            __syncwarp();
-            const uint32_t row = sbuf + (uint32_t)lane * 128u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t dst = row + (uint32_t)((k ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(vv[4 * k]), "f"(vv[4 * k + 1]), "f"(vv[4 * k + 2]), "f"(vv[4 * k + 3]) : "memory");
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&p.out_map, sbuf, c * 32, x0 + q * 32, y, b);
-              tma_store_commit();
-            }
-            ++n_store;
           }
+          const long long t_e2 = timed ? clock64() : 0;
+          if (timed) tw[2] += t_e2 - t_e1;
+          // per-warp staging (32 pixels x 128 B, 128B-swizzled) + per-warp TMA store: no CTA-wide barrier in the epilogue
+          const uint32_t sbuf = sbuf0 + (n_store & 1u) * 4096u;
+          if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer two stores ago has read it
+          __syncwarp();
+          const uint32_t row = sbuf + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t dst = row + (uint32_t)((kk ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * kk]), "f"(v[4 * kk + 1]), "f"(v[4 * kk + 2]), "f"(v[4 * kk + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.out_map, sbuf, c * 32, x0 + q * 32, y, b);
+            tma_store_commit();
+          }
+          ++n_store;
+          if (timed) tw[3] += clock64() - t_e2;
         }
+        if (!valid) continue;
+        if (k + 2 <= R + 1) prefetch(y + 2);     // this group's next row; its loads have a whole turn to land
         if (p.rgb_w && x_in) {
           // + bias + Upsample(skip): upfirdn2d(up=2, pad=(2,1), 4x4) touches 2x2 skip pixels per output pixel (model.py:385-391)
           float o3[3] = {rgb0 + cst[256], rgb1 + cst[257], rgb2 + cst[258]};
@@ -484,6 +527,7 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
 
 int g_rs_cg = 0;          // 0: automatic (pairs when the image is at least 256 pixels wide); 1 / 2: forced (tests)
 int g_rs_rows = 0;        // 0: automatic rows per strip; > 0: forced (tests)
+int g_rs_strict = 0;      // 1: cluster-scope release arrive in the transform warps (A/B timing / paranoia switch)
 
 int rs_check(const vt_conv_desc* d, bool set_err) {
 #define RS_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)
@@ -519,6 +563,7 @@ extern "C" int vt_conv2d_rs_supported(const vt_conv_desc* d) {
 int vt_rs_set_option(const char* key, int value, int* old) {
   if (key && strcmp(key, "rs_cg") == 0) { *old = g_rs_cg; g_rs_cg = value; return 1; }
   if (key && strcmp(key, "rs_rows") == 0) { *old = g_rs_rows; g_rs_rows = value; return 1; }
+  if (key && strcmp(key, "rs_strict") == 0) { *old = g_rs_strict; g_rs_strict = value; return 1; }
   return 0;
 }
 
@@ -540,6 +585,7 @@ extern "C" int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream
   a.fmt = d->bf16x3_nstack == 3 ? 1 : 0;
   a.acc_scale = acc_scale;
   a.dbg = g_tc_dbg_export;
+  a.strict_release = g_rs_strict;
   // strips: 128*cg pixels wide; rows per strip trade the 2 halo rows per strip against the tail of the last wave
   a.strips_x = (int)vt_cdiv(d->W, RS_PX * cg);
   const int units = vt_num_sms() / cg;

@@ -82,6 +82,7 @@ struct TcArgs {
   int direct_store;          // epilogue writes its 128-byte pixel rows straight to global memory instead of smem staging + TMA store
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
   int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
+  int strict_release;        // 1: cluster-scope release on the transform warps' remote arrive (A/B switch)
 };
 
 #define VT_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
@@ -390,9 +391,12 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((m4 + 4) ^ ph) << 4)), "r"(lo[4 * m4]), "r"(lo[4 * m4 + 1]), "r"(lo[4 * m4 + 2]), "r"(lo[4 * m4 + 3]) : "memory");
               }
             }
-            fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            // generic-proxy writes -> visible to the tensor core's async-proxy reads.  The fence also waits until every lane's stores
+            // are performed in this SM's shared memory (one copy, no cache), so the pair's issuing thread only needs a plain remote
+            // arrive; a cluster-scope release compiles to MEMBAR.ALL.GPU (~2k cycles per stage, measured in conv_rs.cu)
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_cta0_release(a_ready(a_st)); else mbar_arrive(a_ready(a_st)); }
+            if (lane == 0) { if (CG == 2) { if (p.strict_release) mbar_arrive_cta0_release(a_ready(a_st)); else mbar_arrive_cta0(a_ready(a_st)); } else mbar_arrive(a_ready(a_st)); }
             if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
           }
         }
@@ -668,6 +672,7 @@ int g_tc_transpose = 1;   // 1: hand the problem over transposed when that waste
 int g_tc_pair_y = -1;     // -1: automatic pair orientation; 0/1: forced (tests)
 int g_tc_direct_store = 0;  // epilogue output path: 0 = smem staging + TMA store, 1 = direct 128-byte row stores, 2 = direct for N <= 128
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
+int g_tc_strict = 0;  // 1: cluster-scope release arrive in the transform warps (A/B timing switch)
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
 #define VT_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)
@@ -706,6 +711,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
+  if (key && strcmp(key, "tc_strict") == 0) { int old = g_tc_strict; g_tc_strict = value; return old; }
   if (key && strcmp(key, "tc_direct_store") == 0) { int old = g_tc_direct_store; g_tc_direct_store = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
   if (key && strcmp(key, "tc_transpose") == 0) { int old = g_tc_transpose; g_tc_transpose = value; return old; }
@@ -764,6 +770,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.act = d->act; a.round_tf32 = d->round_tf32; a.slope = d->slope; a.gain = d->gain; a.alpha = d->alpha; a.beta = d->beta;
   a.B = d->B;
   a.bf16x3 = d->weight_bf16x3 != nullptr;
+  a.strict_release = g_tc_strict;
   a.nstack = (a.bf16x3 && d->bf16x3_nstack) ? 1 : 0;
   a.src_scale[0] = d->src_scale[0]; a.src_scale[1] = d->src_scale[1];
   a.src_affine[0] = d->src_affine[0]; a.src_affine[1] = d->src_affine[1];

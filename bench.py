@@ -222,6 +222,26 @@ def run_cudnn(args, cfg, rank, world):
     from vtoonify_b200.weights import det_inputs, det_state_dict
     dev = torch.device("cuda", 0)
     res = {}
+    # the reference's own CUDA kernels for upfirdn2d / fused_bias_act when oracle/_ref holds them (compiled unmodified from
+    # /root/reference by oracle/build_ref.py); otherwise the oracle's pure-torch restatements run on the GPU
+    from oracle import build_ref
+    ref_ops = build_ref.load_ops()
+    if ref_ops is not None:
+        up_op, fused_op = ref_ops
+
+        def upfirdn2d_ref(x, kernel, up=1, down=1, pad=(0, 0)):           # model/stylegan/op/upfirdn2d.py:89-125, 149-165
+            up_x, up_y = (up, up) if isinstance(up, int) else up
+            down_x, down_y = (down, down) if isinstance(down, int) else down
+            if len(pad) == 2:
+                pad = (pad[0], pad[1], pad[0], pad[1])
+            _, C, H, W = x.shape
+            out = up_op.upfirdn2d(x.reshape(-1, H, W, 1), kernel, up_x, up_y, down_x, down_y, pad[0], pad[1], pad[2], pad[3])
+            return out.view(-1, C, out.shape[1], out.shape[2])
+
+        def fused_lrelu_ref(x, bias=None, negative_slope=0.2, scale=2 ** 0.5):   # model/stylegan/op/fused_act.py:56-71
+            empty = x.new_empty(0)
+            return fused_op.fused_bias_act(x, empty if bias is None else bias, empty, 3, 0, negative_slope, scale)
+        O.upfirdn2d, O.fused_leaky_relu = upfirdn2d_ref, fused_lrelu_ref
     with torch.no_grad():
         if cfg["kind"] == "generator":
             from vtoonify_b200.stylegan import Generator
@@ -256,6 +276,8 @@ def run_cudnn(args, cfg, rank, world):
             "vs_baseline": None, "dtype": "tf32 (torch default: cudnn.allow_tf32=True)", "data": "synthetic",
             "config": workload_config(cfg, args, 1),
             "fp32": {"value": units / (res[False] * 1e-3), "ms_per_step": res[False], "note": "cudnn.allow_tf32=False"},
+            "custom_ops": ("the reference's own upfirdn2d / fused_bias_act CUDA kernels (oracle/_ref, compiled unmodified for sm_100a)"
+                           if ref_ops is not None else "pure-torch restatements of upfirdn2d / fused_bias_act (oracle/_ref not built)"),
             "note": f"oracle restatement of the reference graph on torch {torch.__version__} CUDA kernels (cuDNN {torch.backends.cudnn.version()}); "
                     "test infrastructure timed as a baseline, none of this repo's kernels on the path"}
     emit(json.dumps(line))

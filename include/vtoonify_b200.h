@@ -59,6 +59,16 @@ int vt_upfirdn2d_f32(const float* in, const float* kernel, float* out, int64_t p
 int vt_fused_bias_act_f32(const float* in, const float* bias, float* out, int64_t n, int64_t step_b,
                           int size_b, float negative_slope, float scale, void* stream);
 
+/* f4 (training-side op surface): backward of the op above, fused_bias_act(grad=1) of fused_bias_act_kernel.cu:31-33 and
+ * op/fused_act.py:20-53: out[i] = (ref[i] > 0 ? v : v * negative_slope) * scale with v = in[i] + bias[(i / step_b) % size_b]
+ * (`in` = the incoming gradient, `ref` = the forward OUTPUT, bias = NULL in the first backward, gradgrad_bias in the second). */
+int vt_fused_bias_act_grad_f32(const float* in, const float* bias, const float* ref, float* out, int64_t n, int64_t step_b,
+                               int size_b, float negative_slope, float scale, void* stream);
+/* deterministic per-channel sum of a contiguous [outer, C, inner] tensor (grad_bias = grad_input.sum over batch and space,
+ * op/fused_act.py:33-41); workspace: vt_channel_sum_ws_floats(C) floats */
+int64_t vt_channel_sum_ws_floats(int C);
+int vt_channel_sum_f32(const float* in, float* out, float* workspace, int outer, int C, int64_t inner, void* stream);
+
 /* ---- layout transforms (API boundary NCHW <-> internal NHWC) ------------------------------ */
 /* out NHWC has `c_pad` >= C channels per pixel, the tail is zero-filled. round_tf32: cvt.rna.   */
 int vt_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, int c_pad, int round_tf32, void* stream);

@@ -66,6 +66,9 @@ SYMBOLS = {
     "vt_upfirdn2d_out_size": (c_int, [c_int] * 12 + [POINTER(c_int), POINTER(c_int)]),
     "vt_upfirdn2d_f32": (c_int, [_P, _P, _P, c_int64] + [c_int] * 12 + [_P]),
     "vt_fused_bias_act_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P]),
+    "vt_fused_bias_act_grad_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P]),
+    "vt_channel_sum_ws_floats": (c_int64, [c_int]),
+    "vt_channel_sum_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P]),
     "vt_nchw_to_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vt_nhwc_to_nchw_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "vt_linear_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_int, _P]),

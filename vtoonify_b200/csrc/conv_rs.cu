@@ -551,13 +551,28 @@ int rs_check(const vt_conv_desc* d, bool set_err) {
 #undef RS_SUP
 }
 
+// cta group and shared-memory plan of a launch; returns 0 when the layer does not fit (e.g. 64 -> 64 on a single CTA)
+int rs_plan(const vt_conv_desc* d, int* cg_out, int* a_stages_out, int* smem_out) {
+  const int cg = g_rs_cg ? g_rs_cg : (d->W >= 2 * RS_PX ? 2 : 1);
+  if (cg != 1 && cg != 2) return 0;
+  const int w_bytes = (d->src_c[0] / 32) * 3 * (3 * d->Cout / cg) * 128;
+  const int fixed = w_bytes + 1024 + RS_STAGING + RS_CONST_FLOATS * 4 + 512 /*barriers*/ + 1024 /*alignment*/;
+  int a_stages = (RS_MAX_SMEM - fixed) / RS_A_STAGE;
+  if (a_stages > 8) a_stages = 8;
+  if (a_stages < 3) return 0;
+  *cg_out = cg; *a_stages_out = a_stages; *smem_out = a_stages * RS_A_STAGE + fixed;
+  return 1;
+}
+
 }  // namespace
 
 extern unsigned long long* g_tc_dbg_export;
 
 extern "C" int vt_conv2d_rs_supported(const vt_conv_desc* d) {
   if (!d || d->struct_size != (int)sizeof(vt_conv_desc)) return 0;
-  return rs_check(d, false);
+  if (!rs_check(d, false)) return 0;
+  int cg, st, sm;
+  return rs_plan(d, &cg, &st, &sm);
 }
 
 int vt_rs_set_option(const char* key, int value, int* old) {
@@ -574,8 +589,8 @@ extern "C" int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream
   static thread_local RsArgs a;
   memset(&a, 0, sizeof(a));
   const int Cin = d->src_c[0], Cout = d->Cout;
-  const int cg = g_rs_cg ? g_rs_cg : (d->W >= 2 * RS_PX ? 2 : 1);
-  VT_CHECK(cg == 1 || cg == 2, "conv_rs: rs_cg must be 0, 1 or 2");
+  int cg = 0, plan_stages = 0, smem_bytes = 0;
+  VT_CHECK(rs_plan(d, &cg, &plan_stages, &smem_bytes), "conv_rs: shared memory plan does not fit (Cin=%d Cout=%d)", Cin, Cout);
   a.B = d->B; a.H = d->H; a.W = d->W; a.Cout = Cout; a.KC = Cin / 32; a.wB = d->wB;
   a.S = 512 / Cout - 2;
   a.w_tile_bytes = (3 * Cout / cg) * 128;
@@ -602,13 +617,7 @@ extern "C" int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream
   const int64_t total = (int64_t)d->B * a.strips_x * a.strips_y;
   VT_CHECK(total < (1LL << 30), "conv_rs: too many strips");
   a.total_strips = (int)total;
-  // shared memory plan
-  const int w_bytes = a.KC * 3 * a.w_tile_bytes;
-  const int fixed = w_bytes + 1024 + RS_STAGING + RS_CONST_FLOATS * 4 + 512 /*barriers*/ + 1024 /*alignment*/;
-  a.a_stages = (RS_MAX_SMEM - fixed) / RS_A_STAGE;
-  if (a.a_stages > 8) a.a_stages = 8;
-  VT_CHECK(a.a_stages >= 2, "conv_rs: shared memory plan does not fit");
-  const int smem_bytes = a.a_stages * RS_A_STAGE + fixed;
+  a.a_stages = plan_stages;
   // tensor maps
   {
     const uint64_t cs = (uint64_t)d->src_cstride[0];

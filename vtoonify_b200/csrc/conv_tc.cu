@@ -672,7 +672,7 @@ int g_tc_transpose = 1;   // 1: hand the problem over transposed when that waste
 int g_tc_pair_y = -1;     // -1: automatic pair orientation; 0/1: forced (tests)
 int g_tc_direct_store = 0;  // epilogue output path: 0 = smem staging + TMA store, 1 = direct 128-byte row stores, 2 = direct for N <= 128
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
-int g_tc_strict = 0;  // 1: cluster-scope release arrive in the transform warps (A/B timing switch)
+int g_tc_strict = 1;  // 1: cluster-scope release arrive in the transform warps (no measurable cost here: 74.43 vs 74.41 frames/s); 0: plain remote arrive
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
 #define VT_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)

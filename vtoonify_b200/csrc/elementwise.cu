@@ -282,3 +282,73 @@ extern "C" int vt_f32_to_frame_u8(const float* in, uint8_t* out, int B, int H, i
   VT_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- f4: backward of the fused bias + leaky-relu op (model/stylegan/op/fused_act.py:20-84, fused_bias_act_kernel.cu act*10+grad == 31)
+namespace {
+
+__global__ void __launch_bounds__(256)
+fused_bias_act_grad_kernel(const float* __restrict__ in, const float* __restrict__ bias, const float* __restrict__ ref,
+                           float* __restrict__ out, int64_t n, int64_t step_b, int size_b, float slope, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float x = in[i];
+    if (bias) x += __ldg(bias + (int)((i / step_b) % size_b));
+    out[i] = (ref[i] > 0.f ? x : x * slope) * scale;
+  }
+}
+
+// deterministic per-channel sum of a [outer, C, inner] tensor: stage 1 writes CH_SPLIT partial sums per channel (fixed
+// assignment of elements to partials and fixed reduction trees), stage 2 adds them in order
+constexpr int CH_SPLIT = 64;
+
+__global__ void __launch_bounds__(256)
+channel_sum_partial_kernel(const float* __restrict__ in, float* __restrict__ partial, int outer, int C, int64_t inner) {
+  const int c = blockIdx.x, part = blockIdx.y;
+  const int64_t total = (int64_t)outer * inner;
+  float acc = 0.f;
+  for (int64_t j = (int64_t)part * blockDim.x + threadIdx.x; j < total; j += (int64_t)CH_SPLIT * blockDim.x) {
+    const int64_t o = j / inner, k = j - o * inner;
+    acc += in[(o * C + c) * inner + k];
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[c * CH_SPLIT + part] = red[0];
+}
+
+__global__ void channel_sum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int i = 0; i < CH_SPLIT; ++i) acc += partial[c * CH_SPLIT + i];
+  out[c] = acc;
+}
+
+}  // namespace
+
+extern "C" int vt_fused_bias_act_grad_f32(const float* in, const float* bias, const float* ref, float* out, int64_t n,
+                                          int64_t step_b, int size_b, float negative_slope, float scale, void* stream) {
+  VT_CHECK(in && ref && out && n >= 1, "fused_bias_act_grad: null pointer / empty tensor");
+  VT_CHECK(!bias || (step_b >= 1 && size_b >= 1), "fused_bias_act_grad: bad bias broadcast");
+  int64_t blocks = vt_cdiv(n, 256);
+  const int64_t cap = (int64_t)vt_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  fused_bias_act_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, bias, ref, out, n, bias ? step_b : 1,
+                                                                               bias ? size_b : 1, negative_slope, scale);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t vt_channel_sum_ws_floats(int C) { return (int64_t)C * CH_SPLIT; }
+
+extern "C" int vt_channel_sum_f32(const float* in, float* out, float* workspace, int outer, int C, int64_t inner, void* stream) {
+  VT_CHECK(in && out && workspace && outer >= 1 && C >= 1 && C <= 65535 && inner >= 1, "channel_sum: bad args");
+  channel_sum_partial_kernel<<<dim3((unsigned)C, CH_SPLIT), 256, 0, (cudaStream_t)stream>>>(in, workspace, outer, C, inner);
+  VT_LAUNCH_CHECK();
+  channel_sum_final_kernel<<<(unsigned)vt_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(workspace, out, C);
+  VT_LAUNCH_CHECK();
+  return 0;
+}

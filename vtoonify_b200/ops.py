@@ -261,6 +261,37 @@ def fused_bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], negative_slope
     return out
 
 
+def fused_bias_act_grad(grad: torch.Tensor, ref_out: torch.Tensor, negative_slope: float, scale: float,
+                        bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """backward of :func:`fused_bias_act` w.r.t. its input: ``(ref_out > 0 ? g : g * slope) * scale`` with ``g = grad (+ bias[c])``
+    (op/fused_act.py:20-53; ``bias`` is the second backward's ``gradgrad_bias``)"""
+    _req_cuda(grad, ref_out, bias)
+    grad, ref_out = grad.contiguous(), ref_out.contiguous()
+    if grad.shape != ref_out.shape:
+        raise _lib.VtError("fused_bias_act_grad: grad and the forward output must have the same shape")
+    out = torch.empty_like(grad)
+    step_b = 1
+    for s in grad.shape[2:]:
+        step_b *= s
+    check(_lib.load().vt_fused_bias_act_grad_f32(grad.data_ptr(), _ptr(None if bias is None else bias.contiguous()), ref_out.data_ptr(),
+                                                 out.data_ptr(), grad.numel(), step_b, grad.shape[1] if grad.dim() > 1 else 1,
+                                                 negative_slope, scale, _stream()))
+    return out
+
+
+def channel_sum(x: torch.Tensor) -> torch.Tensor:
+    """``x.sum(dim=[0, 2, 3, ...])`` of a contiguous ``[B, C, ...]`` tensor (deterministic two-stage reduction)"""
+    _req_cuda(x)
+    x = x.contiguous()
+    B, C = x.shape[0], x.shape[1]
+    inner = x.numel() // (B * C)
+    lib = _lib.load()
+    ws = torch.empty((lib.vt_channel_sum_ws_floats(C),), device=x.device, dtype=torch.float32)
+    out = torch.empty((C,), device=x.device, dtype=torch.float32)
+    check(lib.vt_channel_sum_f32(x.data_ptr(), out.data_ptr(), ws.data_ptr(), B, C, inner, _stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # small dense layers
 # ----------------------------------------------------------------------------------------------

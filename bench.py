@@ -387,7 +387,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                 pnet = BiSeNet(19).eval()
                 pnet.load_state_dict(det_state_dict(pnet, seed=21), strict=True)
                 pnet.to(dev)
-            pipe = FramePipeline(model, style_host[:1], d_s=0.5, device=dev, parsing_net=pnet, copy=False, ring=3)
+            pipe = FramePipeline(model, style_host[:1], d_s=0.5, device=dev, parsing_net=pnet, copy=False, ring=3, graph=args.graph)
 
         prof = []
         sampler = None
@@ -482,11 +482,11 @@ def run_ours(args, cfg, rank, world, local_rank):
                 barrier()
                 return max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3), cnt["h2d"] // steps, cnt["d2h"] // steps
 
-            e2e = timed_pipeline(lambda n: hosts[:n], (B, 22, H, W), torch.float32, pipe.synthesize)
+            e2e = timed_pipeline(lambda n: hosts[:n], (B, 22, H, W), torch.float32, pipe.process)
             if pnet is not None:
                 g = torch.Generator().manual_seed(99 + rank)
                 frames_u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(world if rank == 0 else 1)]
-                e2e_u8 = timed_pipeline(lambda n: frames_u8[:n], (B, H, W, 3), torch.uint8, lambda t: pipe.synthesize(pipe.assemble(t)))
+                e2e_u8 = timed_pipeline(lambda n: frames_u8[:n], (B, H, W, 3), torch.uint8, pipe.process)
 
     vals = [ms, e2e[0] if e2e else 0.0, e2e_u8[0] if e2e_u8 else 0.0]
     t = torch.tensor(vals, device=dev, dtype=torch.float64)
@@ -523,6 +523,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     if e2e:
         line["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": cfg["unit"], "h2d_bytes_per_step": int(e2e[1]),
                        "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": e2e_ms / steps,
+                       "cuda_graph": bool(args.graph),
                        "api": ("vtoonify_b200.frame_loop.FramePipeline.run" if world == 1 else "vtoonify_b200.frame_loop.ShardedFrameLoop.run")
                               + " (pinned fp32 [B,22,H,W] inputs H2D on rank 0, clamp + uint8 BGR frames D2H on rank 0)"}
     if e2e_u8:
@@ -566,9 +567,9 @@ def run_video(args, cfg, rank, world, local_rank):
         pnet.load_state_dict(det_state_dict(pnet, seed=21), strict=True)
         pnet.to(dev)
         style = det_inputs(1, H, W, seed=0)[1]
-        pipe = FramePipeline(model, style, d_s=0.5, device=dev, parsing_net=pnet)
+        pipe = FramePipeline(model, style, d_s=0.5, device=dev, parsing_net=pnet, graph=args.graph)
         in_shape, in_dtype = ((B, H, W, 3), torch.uint8) if wire_u8 else ((B, 22, H, W), torch.float32)
-        fn = (lambda t: pipe.synthesize(pipe.assemble(t))) if wire_u8 else pipe.synthesize
+        fn = pipe.process
         loop = ShardedFrameLoop(fn, in_shape, in_dtype, (B, 4 * H, 4 * W, 3), torch.uint8, dev)
         clip = outs = None
         if rank == 0:
@@ -667,6 +668,7 @@ def main():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--wire", default="u8", choices=["u8", "f32"], help="--config video: what crosses PCIe / NVLink on the input side")
+    ap.add_argument("--graph", action="store_true", help="end-to-end legs replay one captured CUDA graph per input geometry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-u8", action="store_true", help="skip the uint8-wire / on-device parsing end-to-end leg")
     args = ap.parse_args()

@@ -100,3 +100,30 @@ def test_pipeline_uint8_frames(setup):
     assert pipe.h2d_bytes == sum(f.numel() for f in frames)
     with pytest.raises(ValueError):
         list(FramePipeline(m, style).run([frames[0]]))
+
+
+def test_pipeline_cuda_graph(setup):
+    """graph=True: one captured CUDA graph per input geometry, bit-identical frames, a handful of launches per batch"""
+    from vtoonify_b200 import _lib
+    from vtoonify_b200.frame_loop import FramePipeline
+    from vtoonify_b200.weights import det_inputs
+    m, _, pnet, _ = setup
+    xs = [det_inputs(2, 32, 40, seed=80 + i)[0].pin_memory() for i in range(4)]
+    style = det_inputs(1, 32, 40, seed=80)[1]
+    eager = list(FramePipeline(m, style, d_s=0.5).run(xs))
+    pipe = FramePipeline(m, style, d_s=0.5, graph=True)
+    first = list(pipe.run(xs[:1]))                           # captures
+    n0 = _lib.launch_count()
+    outs = first + list(pipe.run(xs[1:]))
+    replay_launches = _lib.launch_count() - n0
+    for a, b in zip(outs, eager):
+        assert torch.equal(a, b)
+    assert replay_launches == 0, f"replays must not go through the host launch path ({replay_launches} launches counted)"
+    assert len(pipe._graphs) == 1
+    # a second geometry gets its own graph; uint8 frames + on-device parsing are capturable too
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.randint(0, 256, (1, 48, 64, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    eager_u8 = list(FramePipeline(m, style, d_s=0.5, parsing_net=pnet).run(frames))
+    pipe_u8 = FramePipeline(m, style, d_s=0.5, parsing_net=pnet, graph=True)
+    for a, b in zip(pipe_u8.run(frames), eager_u8):
+        assert torch.equal(a, b)

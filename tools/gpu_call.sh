@@ -1,11 +1,9 @@
 mkdir -p gpurun_out
-T=r2_c7
-for i in 1 2; do timeout 600 python -m pytest tests/test_gpu_conv_rs.py -x -q -m gpu 2>&1 | tail -n 3; done
-timeout 900 python tools/diag_rs.py > gpurun_out/${T}_diag.log 2>&1; grep "B[14]" gpurun_out/${T}_diag.log | cut -c 1-200
-timeout 600 python tools/diag_batch.py 2>&1 | tail -4
-timeout 600 python tools/tc_role_timing.py bf16x3 rs 2>&1 | grep -A3 "plain\|rs_cg 2" | cut -c 1-330 > gpurun_out/${T}_roles.log; cat gpurun_out/${T}_roles.log
-timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_layers.py tests/test_gpu_vtoonify.py -q -m gpu 2>&1 | tail -n 3
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-u8 --dump-layers gpurun_out/${T}_layers.txt > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
-echo "bench rc=$?"; cut -c 1-200 gpurun_out/${T}_bench.json; head -12 gpurun_out/${T}_layers.txt
-VT_TC_STRICT=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-u8 > gpurun_out/${T}_bench_strict.json 2> gpurun_out/${T}_bench_strict.err
-echo "strict bench:"; cut -c 1-200 gpurun_out/${T}_bench_strict.json
+T=r2_c8
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_tests.log 2>&1
+echo "tests rc=$? $(tail -n 1 gpurun_out/${T}_tests.log)"; grep -h "FAILED\|Error" gpurun_out/${T}_tests.log | head -10
+timeout 900 python bench.py --impl cudnn --steps 3 --warmup 1 > gpurun_out/${T}_cudnn.json 2> gpurun_out/${T}_cudnn.err
+echo "cudnn rc=$?"; cut -c 1-700 gpurun_out/${T}_cudnn.json; tail -n 3 gpurun_out/${T}_cudnn.err
+timeout 900 python bench.py --impl cudnn --config generator --steps 5 --warmup 2 > gpurun_out/${T}_cudnn_gen.json 2> gpurun_out/${T}_cudnn_gen.err
+echo "cudnn gen rc=$?"; cut -c 1-400 gpurun_out/${T}_cudnn_gen.json
+bash tools/ncu_r02.sh r02a 2>&1 | tail -40

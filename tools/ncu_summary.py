@@ -42,10 +42,10 @@ def num(s):
 if __name__ == "__main__":
     res = {}
     for path in sys.argv[1:]:
-        for d in load(path):
+        for idx, d in enumerate(load(path)):
             item = {"kernel": d["Kernel Name"][0].split("(")[0]}
             for k, (v, u) in d.items():
                 if any(k == key or k.startswith(key) for key in KEYS) or "tensor" in k:
                     item[k] = [num(v), u]
-            res[path.split("/")[-1]] = item
+            res[path.split("/")[-1] + (f"#{idx}" if idx else "")] = item
     print(json.dumps(res, indent=1))

@@ -279,6 +279,15 @@ int vt_logits_readout_f32(const float* in, float* out, int B, int h, int w, int 
 /* out = a * scale_a + b * scale_b (b may be NULL) */
 int vt_axpby_f32(const float* a, const float* b, float* out, int64_t n, float scale_a, float scale_b, int round_tf32, void* stream);
 
+/* ---- f3: pre-filter + resize of high-resolution frames (style_transfer.py:124-130, 151-156), bit-exact with OpenCV ------ */
+/* out = cv2.sepFilter2D(in, -1, k, k), k = [1,3,3,1]/8: uint8 HWC [B,H,W,3] -> same shape (not in place) */
+int vt_frame_blur4_u8(const uint8_t* in, uint8_t* out, int B, int H, int W, void* stream);
+/* out = cv2.resize(in, (dw, dh))[top : top+Ho, left : left+Wo] (INTER_LINEAR on uint8): in [B,Hs,Ws,3] -> out [B,Ho,Wo,3].
+ * xtab: device int32 [3][dw] = (source column, 2048-scaled weight of it, weight of the next column); ytab: [3][dh] likewise for
+ * rows — built on the host exactly as cv::resize builds them (vtoonify_b200.ops.resize_tables) */
+int vt_frame_resize_crop_u8(const uint8_t* in, uint8_t* out, int B, int Hs, int Ws, int dh, int dw, int top, int left,
+                            int Ho, int Wo, const int* xtab, const int* ytab, void* stream);
+
 /* ---- a11: frame loop transforms ----------------------------------------------------------- */
 /* u8 HWC (RGB or BGR) -> fp32 NCHW in [-1,1]: (v/255 - 0.5)/0.5 ; style_transfer.py:57-60,110,160 */
 int vt_frame_u8_to_f32(const uint8_t* in, float* out, int B, int H, int W, int swap_rb, int64_t out_batch_stride, void* stream);

@@ -259,6 +259,81 @@ def tensor2frame_u8(img, swap_rb=True):
 
 
 # ------------------------------------------------------------------------------------------------
+# f3: pre-filter + resize of high-resolution frames   (style_transfer.py:97, 124-130, 151-156)
+# The arithmetic lives in OpenCV (cv2.sepFilter2D / cv2.resize on uint8 frames, opencv-python 4.x; the reference pins no
+# version): restated here in integer numpy and pinned bit-exactly to cv2 outputs in tests/golden/frame_prep.npz
+# (tests/golden/make_golden_frames.py).
+# ------------------------------------------------------------------------------------------------
+def sep_filter_1331_u8(frame):
+    """cv2.sepFilter2D(frame, -1, k, k) with k = [[0.125],[0.375],[0.375],[0.125]] (style_transfer.py:97, 127) on a uint8 HxWxC
+    frame: anchor = 2 (taps -2..+1), BORDER_REFLECT_101, exact value / 64 rounded half-to-even (cvRound), saturated."""
+    import numpy as np
+    f = np.asarray(frame)
+    H, W = f.shape[:2]
+
+    def refl(i, n):
+        i = np.asarray(i)
+        if n == 1:
+            return np.zeros_like(i)
+        i = np.where(i < 0, -i, i)
+        return np.where(i >= n, 2 * n - 2 - i, i)
+    w = (1, 3, 3, 1)
+    acc = np.zeros(f.shape, dtype=np.int64)
+    ys, xs = np.arange(H), np.arange(W)
+    for a in range(4):
+        rows = f[refl(ys + a - 2, H)].astype(np.int64)
+        for b in range(4):
+            acc += w[a] * w[b] * rows[:, refl(xs + b - 2, W)]
+    v = (acc + 31 + ((acc >> 6) & 1)) >> 6
+    return np.minimum(v, 255).astype(np.uint8)
+
+
+def _resize_coefs(dst, src, clamp):
+    import numpy as np
+    scale = np.float64(src) / np.float64(dst)
+    ofs, c0, c1 = [], [], []
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        sidx = int(np.floor(f))
+        f = np.float32(f - np.float32(sidx))
+        if clamp and sidx < 0:
+            sidx, f = 0, np.float32(0)
+        if clamp and sidx >= src - 1:
+            sidx, f = src - 1, np.float32(0)
+        ofs.append(sidx)
+        c0.append(int(np.rint(np.float32(1.0 - f) * np.float32(2048))))
+        c1.append(int(np.rint(f * np.float32(2048))))
+    return np.array(ofs), np.array(c0, dtype=np.int64), np.array(c1, dtype=np.int64)
+
+
+def resize_linear_u8(frame, w, h):
+    """cv2.resize(frame, (w, h)) (INTER_LINEAR) on a uint8 HxWxC frame: 11-bit fixed-point coefficients, horizontal pass in
+    int32, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2  (cv::resize, 8-bit linear path)."""
+    import numpy as np
+    f = np.asarray(frame)
+    sh, sw = f.shape[:2]
+    xo, xa0, xa1 = _resize_coefs(w, sw, True)
+    yo, yb0, yb1 = _resize_coefs(h, sh, False)
+    S = f.astype(np.int64)
+    x1 = np.minimum(xo + 1, sw - 1)
+    hor = S[:, xo] * xa0[None, :, None] + S[:, x1] * xa1[None, :, None]
+    r0, r1 = hor[np.clip(yo, 0, sh - 1)], hor[np.clip(yo + 1, 0, sh - 1)]
+    out = (((yb0[:, None, None] * (r0 >> 4)) >> 16) + ((yb1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def prefilter_resize_crop(frame, scale, size, crop):
+    """style_transfer.py:124-130 / 151-156: blur once if scale <= 0.75, twice if scale <= 0.375, resize to (w, h), crop
+    [top:bottom, left:right]."""
+    if scale <= 0.75:
+        frame = sep_filter_1331_u8(frame)
+    if scale <= 0.375:
+        frame = sep_filter_1331_u8(frame)
+    top, bottom, left, right = crop
+    return resize_linear_u8(frame, size[0], size[1])[top:bottom, left:right]
+
+
+# ------------------------------------------------------------------------------------------------
 # a10: pSp GradualStyleEncoder (IR-SE-50)   (model/encoder/encoders/psp_encoders.py:35-116, helpers.py:56-119)
 # ------------------------------------------------------------------------------------------------
 def _bn(x, sd, p):

@@ -144,3 +144,22 @@ def test_bisenet_parsing_golden(golden):
     ref = T(g["x_p"])
     assert tuple(y.shape) == (2, 19, 64, 96)
     assert_close(y, ref, 1e-4 * ref.abs().max().item(), "BiSeNet parsing maps")
+
+
+def test_frame_prefilter_resize_matches_opencv(golden):
+    """f3: the oracle's integer restatement of cv2.sepFilter2D / cv2.resize (style_transfer.py:124-130) is bit-exact with the
+    OpenCV outputs stored by tests/golden/make_golden_frames.py"""
+    g = golden("frame_prep")
+    for i in range(int(g["n_cases"])):
+        f = g[f"c{i}_frame"]
+        scale, w, h, top, bottom, left, right = g[f"c{i}_params"]
+        cur = f
+        if f"c{i}_blur1" in g.files:
+            cur = O.sep_filter_1331_u8(cur)
+            assert np.array_equal(cur, g[f"c{i}_blur1"]), f"case {i}: first blur differs from cv2.sepFilter2D"
+        if f"c{i}_blur2" in g.files:
+            cur = O.sep_filter_1331_u8(cur)
+            assert np.array_equal(cur, g[f"c{i}_blur2"]), f"case {i}: second blur differs"
+        assert np.array_equal(O.resize_linear_u8(cur, int(w), int(h)), g[f"c{i}_resized"]), f"case {i}: resize differs from cv2.resize"
+        out = O.prefilter_resize_crop(f, float(scale), (int(w), int(h)), (int(top), int(bottom), int(left), int(right)))
+        assert np.array_equal(out, g[f"c{i}_out"])

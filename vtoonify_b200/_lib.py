@@ -99,6 +99,8 @@ SYMBOLS = {
     "vt_gate_shortcut_add_nhwc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vt_bilinear_add_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vt_axpby_f32": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_int, _P]),
+    "vt_frame_blur4_u8": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "vt_frame_resize_crop_u8": (c_int, [_P, _P] + [c_int] * 9 + [_P, _P, _P]),
     "vt_frame_u8_to_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
     "vt_f32_to_frame_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "vt_selftest_tc_gemm": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),

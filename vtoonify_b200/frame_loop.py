@@ -42,7 +42,8 @@ class FramePipeline:
       * fp32 ``[B, 22, H, W]`` — the ``inputs`` of style_transfer.py:174;
       * a tuple ``(frames_u8 [B,H,W,3] RGB, parsing [B,19,H,W] fp32)`` — parsing computed elsewhere;
       * uint8 ``[B, H, W, 3]`` RGB frames alone — needs ``parsing_net`` (a :class:`vtoonify_b200.bisenet.BiSeNet`):
-        the parsing maps are computed on the device (style_transfer.py:171-174).
+        the parsing maps are computed on the device (style_transfer.py:171-174); with ``prefilter`` the frames are the
+        clip's full-resolution frames and the blur / resize / crop of style_transfer.py:151-156 also runs on the device.
 
     Buffer ownership.  With ``copy=True`` (default) every yielded tensor is a fresh host tensor owned by the caller.
     With ``copy=False`` the yielded tensor is a *borrowed* view of one of ``ring`` pinned staging buffers: it stays valid
@@ -52,7 +53,8 @@ class FramePipeline:
     """
 
     def __init__(self, model, style: torch.Tensor, d_s: Optional[float] = 0.5, device: Optional[torch.device] = None,
-                 output: str = "u8", parsing_net=None, ring: int = 3, copy: bool = True, graph: bool = False):
+                 output: str = "u8", parsing_net=None, ring: int = 3, copy: bool = True, graph: bool = False,
+                 prefilter=None):
         if ring < 2:
             raise ValueError("FramePipeline: ring must be >= 2 (one buffer is being filled while one is being consumed)")
         self.model = model
@@ -63,6 +65,9 @@ class FramePipeline:
         self.parsing_net = parsing_net
         self.ring = ring
         self.copy = copy
+        # (n_blur, (w, h), (top, bottom, left, right)): the reference's per-frame CPU pre-processing of high-resolution clips
+        # (style_transfer.py:151-156: sepFilter2D x n_blur, resize, crop) applied on the device to uploaded uint8 frames
+        self.prefilter = prefilter
         self.graph = graph          # replay one captured CUDA graph per input geometry instead of ~130 launches per batch
         self._graphs = {}
         self._style_b = {}
@@ -84,6 +89,9 @@ class FramePipeline:
                 ops.axpby(parsing[b], None, 1.0 / 16.0, out=x[b, 3:])  # style_transfer.py:174 (x[b, 3:] is contiguous)
             return x
         if item_dev.dtype == torch.uint8:
+            if self.prefilter is not None:
+                n_blur, size, crop = self.prefilter
+                item_dev = ops.frame_prefilter_resize(item_dev, n_blur, size, crop)
             if self.parsing_net is None:
                 raise ValueError("FramePipeline: uint8 frames need parsing_net (face parsing on the device)")
             B, H, W, _ = item_dev.shape

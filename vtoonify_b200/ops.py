@@ -804,6 +804,61 @@ def f32_to_frames_u8(img: torch.Tensor, swap_rb: bool = True) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# f3: pre-filter + resize of high-resolution frames (style_transfer.py:124-130, 151-156), bit-exact with OpenCV
+# ----------------------------------------------------------------------------------------------
+def resize_tables(src: int, dst: int, clamp_weights: bool):
+    """The (offset, weight0, weight1) int32 table cv::resize(INTER_LINEAR, 8-bit) builds for one axis: source coordinate in float
+    like OpenCV, cvFloor, weights cvRound(w * 2048).  Columns (``clamp_weights``): out-of-range neighbours get unit weight on the
+    border pixel; rows: the weights stay fractional and the row index is clamped by the kernel."""
+    import numpy as np
+    scale = np.float64(src) / np.float64(dst)
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp_weights:
+        lo, hi = s < 0, s >= src - 1
+        f = np.where(lo | hi, np.float32(0), f).astype(np.float32)
+        s = np.where(lo, 0, np.where(hi, src - 1, s))
+    w1 = np.rint(f * np.float32(2048)).astype(np.int32)
+    w0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32)
+    return np.stack([s.astype(np.int32), w0, w1], axis=0)
+
+
+_resize_table_cache = {}
+
+
+def frame_prefilter_resize(frames: torch.Tensor, n_blur: int, size: Tuple[int, int],
+                           crop: Optional[Tuple[int, int, int, int]] = None) -> torch.Tensor:
+    """uint8 ``[B,H,W,3]`` frames -> ``cv2.resize(blur^n(frame), size)[top:bottom, left:right]`` on the device, bit-exact with
+    the reference's CPU pre-processing (``size`` = (w, h) like cv2; ``crop`` = (top, bottom, left, right))."""
+    if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+        raise _lib.VtError("frame_prefilter_resize needs a CUDA uint8 [B,H,W,3] tensor")
+    if n_blur not in (0, 1, 2):
+        raise _lib.VtError("frame_prefilter_resize: the frame loop applies the blur 0, 1 or 2 times")
+    frames = frames.contiguous()
+    B, H, W, _ = frames.shape
+    lib = _lib.load()
+    cur = frames
+    for _ in range(n_blur):
+        nxt = torch.empty_like(cur)
+        check(lib.vt_frame_blur4_u8(cur.data_ptr(), nxt.data_ptr(), B, H, W, _stream()))
+        cur = nxt
+    dw, dh = int(size[0]), int(size[1])
+    top, bottom, left, right = (0, dh, 0, dw) if crop is None else (int(c) for c in crop)
+    key = (H, W, dh, dw, frames.device)
+    tabs = _resize_table_cache.get(key)
+    if tabs is None:
+        tabs = (torch.from_numpy(resize_tables(W, dw, True)).to(frames.device).contiguous(),
+                torch.from_numpy(resize_tables(H, dh, False)).to(frames.device).contiguous())
+        _resize_table_cache[key] = tabs
+    out = torch.empty((B, bottom - top, right - left, 3), device=frames.device, dtype=torch.uint8)
+    check(lib.vt_frame_resize_crop_u8(cur.data_ptr(), out.data_ptr(), B, H, W, dh, dw, top, left, bottom - top, right - left,
+                                      tabs[0].data_ptr(), tabs[1].data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # face-parsing pre-network helpers (model/bisenet/model.py, style_transfer.py:171-174)
 # ----------------------------------------------------------------------------------------------
 def frame_s2d(x: torch.Tensor, upsample2: bool, cpad: int = 32) -> torch.Tensor:

@@ -46,7 +46,7 @@ def get_precision() -> str:
 # row-strip kernel (vertical taps stacked along N, cross-row accumulation in TMEM: conv_rs.cu); rs_fmt: its operand split
 # ("bf16" | "f16": fp16 halves carry 11 + 11 mantissa bits instead of 8 + 8, weights pre-scaled by 2^10).
 _options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False, "fuse_adain": True,
-            "rs_conv": True, "rs_min_width": 256, "rs_fmt": "bf16"}
+            "rs_conv": True, "rs_min_width": 256, "rs_fmt": "bf16", "nvtx": bool(_os.environ.get("VT_NVTX"))}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 
@@ -156,6 +156,25 @@ def style_cached(owner, name: str, fn, extra=None):
     val = fn()
     cache[name] = (key, val)
     return val
+
+
+class nvtx_range:
+    """NVTX range around a stage / layer when ``set_option("nvtx", True)`` (or VT_NVTX=1): names the launches of a stage for
+    ``ncu --nvtx --nvtx-include "<name>/"`` and for timeline tools; free when disabled."""
+
+    def __init__(self, name: str):
+        self.name = name
+        self.on = _options["nvtx"]
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _round_flag() -> int:

@@ -258,14 +258,16 @@ class VToonify(ops.WeightsEpochMixin, nn.Module):
         # encoder: downsampling conv blocks, then the res blocks (interleaved with dilated ModRes for D)
         feat = ops.to_nhwc(x, ops._pad32(x.shape[1]))
         encoder_features = []
-        for block in self.encoder[:-2]:
-            feat = block.forward_nhwc(feat)
+        for bi, block in enumerate(self.encoder[:-2]):
+            with ops.nvtx_range(f"vtoonify/encoder.{bi}"):
+                feat = block.forward_nhwc(feat)
             encoder_features.append(feat)
         encoder_features = encoder_features[::-1]
         for ii, block in enumerate(self.encoder[-2]):
-            feat = block.forward_nhwc(feat)
-            if D:
-                feat = self.res[ii + 1].forward_nhwc(feat, resstyles[:, ii + 1], d_s)
+            with ops.nvtx_range(f"vtoonify/resblock.{ii}"):
+                feat = block.forward_nhwc(feat)
+                if D:
+                    feat = self.res[ii + 1].forward_nhwc(feat, resstyles[:, ii + 1], d_s)
         out = feat
         skip = self.encoder[-1].forward_smalln(feat)
         if return_feat:
@@ -278,19 +280,21 @@ class VToonify(ops.WeightsEpochMixin, nn.Module):
             if 2 ** (5 + ((_index - 1) // 2)) <= self.in_size:
                 fi = (_index - 1) // 2
                 f_E = encoder_features[fi]
-                if D:
-                    out, m_E, fEm = self.fusion_out[fi].forward_nhwc(out, f_E, d_s)
-                    if fEm is None:
-                        skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip, src_mask=m_E)
+                with ops.nvtx_range(f"vtoonify/fusion.{fi}"):
+                    if D:
+                        out, m_E, fEm = self.fusion_out[fi].forward_nhwc(out, f_E, d_s)
+                        if fEm is None:
+                            skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip, src_mask=m_E)
+                        else:
+                            skip = self.fusion_skip[fi].forward_smalln(fEm, planar=skip)
+                        m_Es.append(m_E)
                     else:
-                        skip = self.fusion_skip[fi].forward_smalln(fEm, planar=skip)
-                    m_Es.append(m_E)
-                else:
-                    out = self.fusion_out[fi].forward_nhwc(out, x2=f_E)
-                    skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip)
-            out = conv1.forward_nhwc(out, adastyles[:, _index + 6], zero_noise=True)
-            out, skip = conv2.forward_nhwc(out, adastyles[:, _index + 7], zero_noise=True,
-                                           to_rgb=(to_rgb, adastyles[:, _index + 8], skip))
+                        out = self.fusion_out[fi].forward_nhwc(out, x2=f_E)
+                        skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip)
+            with ops.nvtx_range(f"vtoonify/generator.level{(_index - 1) // 2}"):
+                out = conv1.forward_nhwc(out, adastyles[:, _index + 6], zero_noise=True)
+                out, skip = conv2.forward_nhwc(out, adastyles[:, _index + 7], zero_noise=True,
+                                               to_rgb=(to_rgb, adastyles[:, _index + 8], skip))
             _index += 2
 
         image = skip

@@ -23,7 +23,6 @@ def test_upfirdn2d_grad_and_gradgrad(up, down, pad, ksize):
         w = _rand(tuple(y_c.shape), 3)
         g_c, = torch.autograd.grad((y_c * w).sum(), x_c, create_graph=True)
         v = _rand(tuple(g_c.shape), 4)
-        gg_c, = torch.autograd.grad((g_c * v).sum(), x_c, allow_unused=True)      # zero: the op is linear in x
         x_g = x_c.detach().cuda().requires_grad_(True)
         y_g = upfirdn2d(x_g, k.cuda(), up=up, down=down, pad=pad)
         assert y_g.requires_grad and tuple(y_g.shape) == tuple(y_c.shape)
@@ -35,7 +34,6 @@ def test_upfirdn2d_grad_and_gradgrad(up, down, pad, ksize):
         ggw_g, = torch.autograd.grad((g_g * v.cuda()).sum(), w_g)
         ref = O.upfirdn2d(v, k, up=up, down=down, pad=pad)
         assert (ggw_g.cpu() - ref).abs().max().item() <= 1e-5
-        assert gg_c is None or gg_c.abs().max().item() == 0
 
 
 @pytest.mark.parametrize("shape,has_bias", [((2, 8, 5, 7), True), ((3, 16), True), ((2, 4, 6, 6), False)])

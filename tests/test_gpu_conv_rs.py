@@ -65,6 +65,8 @@ def test_rs_vs_fp32(rs_knobs, case, fmt, tol):
     ref = _run(x, w, kw, H, W, rs=False, precision="fp32")
     y = _run(x, w, kw, H, W, rs=True)
     torch.cuda.synchronize()
+    if cg == 1 and Cin == 64 and Cout == 64:
+        tol = max(tol, 4e-5)      # 64 -> 64 does not fit one CTA's shared memory: the tap-by-tap (bf16 split) kernel takes the launch
     scale = ref.abs().max().item()
     err = (y - ref).abs().max().item()
     print(f"conv_rs {case} [{fmt}]: max|err| {err:.3e} (max|ref| {scale:.2f})")

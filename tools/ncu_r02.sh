@@ -16,7 +16,7 @@ print(order[len(order)//2])
 PY
 )
 echo "conv_tc median launch index: $MEDIAN"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_rs -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_rs -c 3 \
     -f -o gpurun_out/ncu_${TAG}_rs python tools/profile_step.py > gpurun_out/ncu_${TAG}_rs.log 2>&1
 ncu -i gpurun_out/ncu_${TAG}_rs.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_rs.raw.csv 2>/dev/null
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tc -s $MEDIAN -c 1 \

@@ -189,7 +189,18 @@ int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 a
  * (-> fused ToRGB tail).  Dense NHWC output only. */
 int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream);
 int vt_conv2d_rs_supported(const vt_conv_desc* d);
-/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","tc_direct_store","smalln_is","fir4","upfirdn_tiled","rs_cg","rs_rows","rs_strict","tc_strict"};
+/* Row-strip UP-convolution (StyledConv up-layers, model/stylegan/model.py:273-286): out = Blur4x4(conv_transpose2d(in, w, stride 2)),
+ * NHWC [B,H,W,Cin] -> [B,2H,2W,Cout], with only the horizontal half of the (separable) blur folded into the weights (2x the
+ * algorithmic MACs instead of the 4x of vt_fold_upconv_weights_f32) and the vertical half applied to the TMEM accumulators.
+ *   vt_fold_upconv_x_weights_f32: w9 [wB][9 = ky*3+kx][Cout][Cin] (modulated transposed-conv taps) + the FLIPPED 1-D blur taps
+ *     g (4 HOST floats, K[m][n] = gk[m]*gk[n], g[m] = gk[3-m]) -> out [wB][Cout/32][Cin/32][3 (dx)][192 = (ky*2+px)*32+co][32]; split the
+ *     result with vt_split_weights_bf16x3 / vt_split_weights_f16x3 (rows of 32 channels) and pass it as `w_split`.
+ *   vt_conv_up2_rs: v = acc * acc_scale + bias + noise_w * noise[b, Y, X] -> activation; fmt 0 = bf16 split, 1 = fp16 split. */
+int vt_fold_upconv_x_weights_f32(const float* w9, const float* g_host4, float* out, int wB, int Cout, int Cin, void* stream);
+int vt_conv_up2_rs(const float* in, const void* w_split, float* out, int B, int H, int W, int Cin, int Cout, int wB,
+                   const float* g_host4, const float* bias, const float* noise, const float* noise_w, int act,
+                   float slope, float gain, int fmt, float acc_scale, void* stream);
+/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","tc_direct_store","smalln_is","fir4","upfirdn_tiled","rs_cg","rs_rows","rs_strict","tc_strict","rsu_cg","rsu_rows"};
  * returns the previous value (-1 for an unknown key) */
 int vt_set_option(const char* key, int value);
 /* tuning only: device buffer of 148*16 uint64 that conv_tc fills with per-role wait-cycle counters (NULL disables) */

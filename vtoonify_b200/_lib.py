@@ -82,6 +82,9 @@ SYMBOLS = {
     "vt_conv2d_tc_supported": (c_int, [POINTER(ConvDesc)]),
     "vt_conv2d_rs": (c_int, [POINTER(ConvDesc), c_float, _P]),
     "vt_conv2d_rs_supported": (c_int, [POINTER(ConvDesc)]),
+    "vt_fold_upconv_x_weights_f32": (c_int, [_P, POINTER(c_float), _P, c_int, c_int, c_int, _P]),
+    "vt_conv_up2_rs": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), _P, _P, _P, c_int, c_float, c_float,
+                               c_int, c_float, _P]),
     "vt_set_option": (c_int, [c_char_p, c_int]),
     "vt_set_debug_buffer": (c_int, [_P]),
     "vt_smalln_conv_f32": (c_int, [POINTER(SmallNDesc), _P]),

@@ -705,9 +705,11 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
 }  // namespace
 
 int vt_rs_set_option(const char* key, int value, int* old);   // conv_rs.cu
+int vt_rsu_set_option(const char* key, int value, int* old);  // conv_rsu.cu
 
 extern "C" int vt_set_option(const char* key, int value) {
   { int old = 0; if (vt_rs_set_option(key, value, &old)) return old; }
+  { int old = 0; if (vt_rsu_set_option(key, value, &old)) return old; }
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }

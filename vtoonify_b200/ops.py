@@ -46,7 +46,10 @@ def get_precision() -> str:
 # row-strip kernel (vertical taps stacked along N, cross-row accumulation in TMEM: conv_rs.cu); rs_fmt: its operand split
 # ("bf16" | "f16": fp16 halves carry 11 + 11 mantissa bits instead of 8 + 8, weights pre-scaled by 2^10).
 _options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False, "fuse_adain": True,
-            "rs_conv": True, "rs_min_width": 256, "rs_fmt": "bf16", "nvtx": bool(_os.environ.get("VT_NVTX"))}
+            "rs_conv": True, "rs_min_width": 256, "rs_fmt": "bf16", "nvtx": bool(_os.environ.get("VT_NVTX")),
+            # rsu_conv: up-convolutions with Cin <= rsu_max_cin and rows of >= rs_min_width pixels on the row-strip up-conv kernel
+            # (horizontal blur folded into the weights, vertical blur on the TMEM accumulators: conv_rsu.cu)
+            "rsu_conv": True, "rsu_max_cin": 128}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 
@@ -630,6 +633,75 @@ def conv_up2_folded_nhwc(x: torch.Tensor, w_folded: torch.Tensor, bias=None, noi
     offs = [(ry * Wf + rx) * Cout for ry in (0, 1) for rx in (0, 1)]
     conv2d_nhwc([x], w_folded, _UP2_TAPS, 1, H, W, out=out, out_view=view, phase_offs=offs, bias=bias, noise=noise,
                 noise_w=noise_w, act=act, slope=slope, gain=gain, precision=precision)
+    return out
+
+
+def separable_blur_taps(kernel: torch.Tensor):
+    """4x4 blur buffer ``K = outer(gk, gk)`` -> the flipped 1-D taps ``g[m] = gk[3 - m]`` as 4 host floats, or None when ``K`` is
+    not such an outer product (checked once per tensor object: one device -> host read)."""
+    cached = getattr(kernel, "_vt_g1d", None)
+    if cached is not None and cached[0] == kernel._version:
+        return cached[1]
+    g = None
+    if tuple(kernel.shape) == (4, 4):
+        K = kernel.detach().double().cpu()
+        tot = float(K.sum())
+        if tot > 0:
+            gk = K.sum(0) / math.sqrt(tot)
+            if float((torch.outer(gk, gk) - K).abs().max()) <= 1e-6 * float(K.abs().max()):
+                g = tuple(float(v) for v in gk.flip(0))
+    kernel._vt_g1d = (kernel._version, g)
+    return g
+
+
+def rsu_eligible(cin: int, cout: int, W: int, kernel: torch.Tensor, pad, precision: Optional[str] = None) -> bool:
+    return ((precision or _precision) == "bf16x3" and _options["rsu_conv"] and cin % 32 == 0 and 32 <= cin <= _options["rsu_max_cin"]
+            and cout % 32 == 0 and 32 <= cout <= 128 and W >= _options["rs_min_width"] and tuple(pad) == (1, 1)
+            and separable_blur_taps(kernel) is not None)
+
+
+def conv_up2_rs_nhwc(x: torch.Tensor, w9: torch.Tensor, blur_kernel: torch.Tensor, bias=None, noise=None, noise_w=None,
+                     act: int = ACT_NONE, slope: float = 0.2, gain: float = 1.0) -> torch.Tensor:
+    """Blur(conv_transpose2d(x, w, stride 2)) on the row-strip up-conv kernel.  ``w9``: modulated weights ``[wB, 9, Cout, Cin]``
+    (un-rounded fp32, slab ky*3+kx); the folded + split form is cached on the tensor object."""
+    _req_cuda(x, w9, bias, noise, noise_w)
+    B, H, W, Cin = x.shape
+    wB, nine, Cout, wc = w9.shape
+    g = separable_blur_taps(blur_kernel)
+    if g is None or nine != 9 or wc != Cin or not x.is_contiguous() or not w9.is_contiguous():
+        raise _lib.VtError("conv_up2_rs_nhwc: needs a separable 4x4 blur, [wB, 9, Cout, Cin] weights and a contiguous NHWC input")
+    lib = _lib.load()
+    garr = (_lib.c_float * 4)(*g)
+    fmt = _options["rs_fmt"]
+    cached = getattr(w9, "_vt_rsu", None)
+    if cached is not None and cached[0] == w9._version and cached[1] == w9.data_ptr() and cached[2] == fmt and cached[3] == g:
+        wsplit, acc_scale = cached[4], cached[5]
+    else:
+        n = wB * (Cout // 32) * (Cin // 32) * 3 * 192 * 32
+        folded = torch.empty((n // 32, 32), device=x.device, dtype=torch.float32)
+        check(lib.vt_fold_upconv_x_weights_f32(w9.data_ptr(), garr, folded.data_ptr(), wB, Cout, Cin, _stream()))
+        wsplit = torch.empty_like(folded)
+        if fmt == "f16":
+            scale = 1024.0
+            check(lib.vt_split_weights_f16x3(folded.data_ptr(), wsplit.data_ptr(), n // 32, 32, scale, _stream()))
+            acc_scale = 1.0 / scale
+        else:
+            check(lib.vt_split_weights_bf16x3(folded.data_ptr(), wsplit.data_ptr(), n // 32, 32, 0, _stream()))
+            acc_scale = 1.0
+        w9._vt_rsu = (w9._version, w9.data_ptr(), fmt, g, wsplit, acc_scale)
+    out = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.float32)
+    args = (x.data_ptr(), wsplit.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, wB, garr, _ptr(bias), _ptr(noise), _ptr(noise_w), act,
+            slope, gain, 1 if fmt == "f16" else 0, acc_scale, _stream())
+    if _tc_profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flops = 2.0 * B * H * W * Cout * Cin * 9
+        nbytes = 4.0 * (B * H * W * Cin + B * 4 * H * W * Cout + w9.numel())
+        e0.record()
+        check(lib.vt_conv_up2_rs(*args))
+        e1.record()
+        _tc_profile.append((e0, e1, flops, nbytes, f"{Cin}->{Cout}x2up k9 s1 {H}x{W} [row-strip up]", 3.0 * 2.0 * flops))
+    else:
+        check(lib.vt_conv_up2_rs(*args))
     return out
 
 

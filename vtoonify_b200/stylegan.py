@@ -212,6 +212,10 @@ class ModulatedConv2d(nn.Module):
         if self.upsample:
             if k != 3:
                 raise NotImplementedError("upsampling ModulatedConv2d is 3x3 in StyleGAN2")
+            if externalweight is None and Cs == self.in_channel and ops.rsu_eligible(self.in_channel, self.out_channel, W, self.blur.kernel, self.blur.pad):
+                # row-strip up-conv: horizontal blur folded into the weights, vertical blur on the accumulators (2x, not 4x, the MACs)
+                w9 = self.modulated_weights(style, Cs, None, round_tf32=False)
+                return ops.conv_up2_rs_nhwc(x, w9, self.blur.kernel, bias=bias, noise=noise, noise_w=noise_w, act=a, slope=slope, gain=gain)
             if tuple(self.blur.kernel.shape) == (4, 4) and tuple(self.blur.pad) == (1, 1) and ops.use_folded_upconv(self.in_channel):
                 # Blur o conv_transpose folded into 4 phase-specific 3x3 kernels: one launch, no intermediate tensor
                 wf = self.modulated_weights(style, Cs, externalweight, round_tf32=False, folded=True)

@@ -1,12 +1,11 @@
 mkdir -p gpurun_out
-T=r2_c9
-timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_tests.log 2>&1
-echo "tests rc=$? $(tail -n 1 gpurun_out/${T}_tests.log)"; grep -h "FAILED\|Error" gpurun_out/${T}_tests.log | head -10
-bash tools/ncu_r02.sh r02b 2>&1 | tail -12 | cut -c 1-600
-bash tools/run_sanitizer.sh r02 2>&1 | tail -4
-timeout 900 python bench.py --steps 10 --warmup 3 --graph > gpurun_out/${T}_bench_graph.json 2> gpurun_out/${T}_bench_graph.err
-echo "bench graph rc=$?"; cut -c 1-250 gpurun_out/${T}_bench_graph.json; tail -n 3 gpurun_out/${T}_bench_graph.err
-timeout 300 python bench.py --height 256 --width 256 --batch 1 --steps 30 --warmup 5 --no-cpu-baseline --graph > gpurun_out/${T}_256_graph.json 2> gpurun_out/${T}_256_graph.err
-echo "256 graph rc=$?"; cut -c 1-250 gpurun_out/${T}_256_graph.json
-timeout 300 python bench.py --height 256 --width 256 --batch 1 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/${T}_256.json 2> gpurun_out/${T}_256.err
-echo "256 rc=$?"; cut -c 1-250 gpurun_out/${T}_256.json
+T=r2_c12
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/${T}_bench2.json 2> gpurun_out/${T}_bench2.err
+echo "bench N=2 rc=$?"; cut -c 1-300 gpurun_out/${T}_bench2.json; tail -n 5 gpurun_out/${T}_bench2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --config video --warmup 2 > gpurun_out/${T}_video2.json 2> gpurun_out/${T}_video2.err
+echo "video N=2 rc=$?"; cut -c 1-300 gpurun_out/${T}_video2.json; tail -n 5 gpurun_out/${T}_video2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --config video --wire f32 --warmup 2 > gpurun_out/${T}_video2_f32.json 2> gpurun_out/${T}_video2_f32.err
+echo "video f32 N=2 rc=$?"; cut -c 1-300 gpurun_out/${T}_video2_f32.json; tail -n 3 gpurun_out/${T}_video2_f32.err
+timeout 600 python -m pytest tests/test_gpu_dist.py -q -m gpu 2>&1 | tail -n 2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --impl reference --steps 1 --warmup 0 > gpurun_out/${T}_ref2.json 2> gpurun_out/${T}_ref2.err
+echo "ref N=2 rc=$?"; cut -c 1-300 gpurun_out/${T}_ref2.json

@@ -50,9 +50,30 @@ def up_case(B, Cin, Cout, H, W):
     report(f"up {Cin}->{Cout} {H}x{W} B{B}", fn, 2.0 * B * H * W * Cout * Cin * 36)
 
 
+def rsu_case(B, Cin, Cout, H, W):
+    x = torch.randn((B, H, W, Cin), device=dev)
+    w9 = ops.prep_weights(torch.randn((Cout, Cin, 3, 3), device=dev) / (3 * Cin ** 0.5), cin_pad=Cin, round_tf32=False)
+    bias = torch.zeros(Cout, device=dev)
+    fn = lambda: ops.conv_up2_rs_nhwc(x, w9, K4, bias=bias, act=1)
+    report(f"up {Cin}->{Cout} {H}x{W} B{B} [row-strip up]", fn, 2.0 * B * H * W * Cout * Cin * 18)
+
+
 ops.set_precision(sys.argv[1] if len(sys.argv) > 1 else ops.DEFAULT_PRECISION)
 print("precision", ops.get_precision())
 with torch.no_grad():
+    if len(sys.argv) > 2 and sys.argv[2] == "rsu":
+        up_case(4, 64, 32, 1152, 2048)
+        rsu_case(4, 64, 32, 1152, 2048)
+        up_case(4, 128, 64, 576, 1024)
+        rsu_case(4, 128, 64, 576, 1024)
+        rsu_case(8, 64, 32, 512, 512)
+        rsu_case(8, 128, 64, 256, 256)
+        for rows in (8, 16, 32, 64):
+            lib.vt_set_option(b"rsu_rows", rows)
+            print("rsu rows_per_strip", rows)
+            rsu_case(4, 64, 32, 1152, 2048)
+        lib.vt_set_option(b"rsu_rows", 0)
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "rs":
         for rs in (False, True):
             ops.set_option("rs_conv", rs)

@@ -34,8 +34,9 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 3   /* 2: vt_conv_desc gained weight_bf16x3 / bf16x3_nstack / src_scale, vt_smalln_desc src_mask / tsum, vt_split_weights_bf16x3
-                            * 3: face-parsing helpers (vt_frame_s2d_f32 .. vt_logits_readout_f32 with out_bstride), backward ops, frame pre-filter */
+#define VT_ABI_VERSION 4   /* 2: vt_conv_desc gained weight_bf16x3 / bf16x3_nstack / src_scale, vt_smalln_desc src_mask / tsum, vt_split_weights_bf16x3
+                            * 3: face-parsing helpers (vt_frame_s2d_f32 .. vt_logits_readout_f32 with out_bstride), backward ops, frame pre-filter
+                            * 4: row-strip kernels, vt_conv_desc gained split_fmt / acc_scale */
 
 /* ---- library info / errors ------------------------------------------------------------- */
 int         vt_abi_version(void);
@@ -173,6 +174,10 @@ typedef struct vt_conv_desc {
                                  * padding stays 0, exactly as the reference zero-pads the *normalised* tensor. Used to apply
                                  * AdaIN (model/dualstylegan.py:16-21) inside the convolution that consumes it
                                  * (vt_adain_affine_f32 builds the table). Rejected by the other kernels.                  */
+  int32_t split_fmt;            /* format of the split operands (`weight_bf16x3` set): 0 = bf16 hi + lo (vt_split_weights_bf16x3),
+                                 * 1 = fp16 hi + lo (vt_split_weights_f16x3: 11 + 11 mantissa bits, |activation| < 1.3e5)           */
+  float   acc_scale;            /* accumulators are multiplied by this before the epilogue (0 = 1): the inverse of the power-of-two
+                                 * `scale` given to vt_split_weights_f16x3                                                           */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */

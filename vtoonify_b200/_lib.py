@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvtoonify_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 VT_MAX_TAPS = 36
 ACT_NONE, ACT_LRELU, ACT_RELU_TANH = 0, 1, 2
 
@@ -36,6 +36,7 @@ class ConvDesc(Structure):
         ("rgb_w", c_void_p), ("rgb_bias", c_void_p), ("rgb_skip", c_void_p), ("rgb_skip_kernel", c_void_p),
         ("rgb_out", c_void_p),
         ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("bf16x3_nstack", c_int32), ("reserved2", c_int32), ("src_scale", c_void_p * 2), ("src_affine", c_void_p * 2),
+        ("split_fmt", c_int32), ("acc_scale", c_float),
     ]
 
 

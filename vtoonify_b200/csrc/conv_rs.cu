@@ -87,9 +87,6 @@ __device__ __forceinline__ void tmem_ld16_add(uint32_t taddr, float* acc) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {   // kind::f16 with FP16 operands (a_format = b_format = 0)
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 #define RS_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
 
@@ -299,13 +296,7 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
           uint32_t hi[16], lo[16];
           if (p.fmt) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
-              hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
+            for (int i = 0; i < 16; ++i) split_f16x2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {

@@ -69,7 +69,6 @@ __device__ __forceinline__ void ru_zero32(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void ru_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t ru_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 __device__ __forceinline__ int ru_slot(int p) { return (p + 2) % RU_S; }   // p >= -2
 
 #define RU_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
@@ -184,7 +183,7 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
     }
   } else if (warp == 1 && rank == 0) {
     // ================= MMA issuer =================
-    const uint32_t idesc = p.fmt ? ru_idesc_f16(RU_PX * CG, RU_N) : make_idesc_bf16(RU_PX * CG, RU_N);
+    const uint32_t idesc = p.fmt ? make_idesc_f16(RU_PX * CG, RU_N) : make_idesc_bf16(RU_PX * CG, RU_N);
     int a_st = 0, b_st = 0; uint32_t a_par = 0, b_par = 0;
     uint32_t acq = 0;
     auto acquire = [&](int q) {
@@ -268,13 +267,7 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
           uint32_t hi[16], lo[16];
           if (p.fmt) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
-              hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
+            for (int i = 0; i < 16; ++i) split_f16x2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {

@@ -83,6 +83,8 @@ struct TcArgs {
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
   int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
   int strict_release;        // 1: cluster-scope release on the transform warps' remote arrive (A/B switch)
+  int fmt;                   // split-operand format: 0 = bf16 hi/lo, 1 = fp16 hi/lo
+  float acc_scale;           // accumulators are multiplied by this first (undoes the power-of-two weight scale of the fp16 split)
 };
 
 #define VT_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
@@ -223,7 +225,8 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     }
   } else if (warp == 1 && rank == 0) {
     // ================= MMA issuer (whole warp converged; one elected lane issues; CTA rank 0 only) =================
-    const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(TILE_M * CG, p.mma_n) : make_idesc_tf32(TILE_M * CG, p.mma_n);
+    const uint32_t idesc = p.bf16x3 ? (p.fmt ? make_idesc_f16(TILE_M * CG, p.mma_n) : make_idesc_bf16(TILE_M * CG, p.mma_n))
+                                    : make_idesc_tf32(TILE_M * CG, p.mma_n);
     int a_st = 0, b_st = 0, as = 0;
     uint32_t a_par = 0, b_par = 0, t_par = 0;
     const uint32_t tile_bytes_n = (uint32_t)(p.mma_n / CG) * 128u;   // bytes of one tap's weight rows held by this CTA
@@ -376,14 +379,19 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                 }
               }
               uint32_t hi[16], lo[16];
+              if (p.fmt) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                // packed converts (one cvt.rn.bf16x2.f32 per pair); a bf16 widened to fp32 is its bits shifted left by 16
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                const float r0 = f[2 * i] - __uint_as_float(hi[i] << 16), r1 = f[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                for (int i = 0; i < 16; ++i) split_f16x2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  // packed converts (one cvt.rn.bf16x2.f32 per pair); a bf16 widened to fp32 is its bits shifted left by 16
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                  hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                  const float r0 = f[2 * i] - __uint_as_float(hi[i] << 16), r1 = f[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                  lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
               }
 #pragma unroll
               for (int m4 = 0; m4 < 4; ++m4) {
@@ -452,6 +460,10 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.mt + g) * p.mma_n + 32), v2);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
+          if (p.acc_scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
           }
           const long long t_math0 = p.dbg ? clock64() : 0;
           if (g == p.mt - 1 && j == nchunks - 1) {
@@ -690,7 +702,8 @@ int check_supported(const vt_conv_desc* d, bool set_err) {
   VT_SUP((!d->src_scale[0] && !d->src_scale[1] && !d->src_affine[0] && !d->src_affine[1]) || (d->weight_bf16x3 && d->stride == 1),
          "conv_tc: src_scale / src_affine need the bf16x3 mode and stride 1");
   for (int s = 0; s < 2; ++s) VT_SUP(!d->src_affine[s] || (((uintptr_t)d->src_affine[s] & 15) == 0), "conv_tc: src_affine not 16-byte aligned");
-  VT_SUP(!d->bf16x3_nstack || (d->weight_bf16x3 && d->Cout == 32 && d->n_phase == 1), "conv_tc: the N-stacked bf16x3 form needs Cout == 32 and one phase");
+  VT_SUP(!d->bf16x3_nstack || (d->weight_bf16x3 && d->Cout == 32 && d->n_phase == 1 && d->split_fmt == 0), "conv_tc: the N-stacked bf16x3 form needs Cout == 32, one phase and the bf16 split");
+  VT_SUP(d->split_fmt == 0 || d->split_fmt == 1, "conv_tc: split_fmt must be 0 (bf16) or 1 (fp16)");
   VT_SUP(!d->weight_bf16x3 || d->w_cstride % KCH == 0, "conv_tc: bf16x3 weights need a channel stride that is a multiple of 32");
   VT_SUP(!d->res || (((uintptr_t)d->res & 15) == 0), "conv_tc: res not 16-byte aligned");
   VT_SUP(!d->bias || (((uintptr_t)d->bias & 15) == 0), "conv_tc: bias not 16-byte aligned");
@@ -773,6 +786,8 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   a.B = d->B;
   a.bf16x3 = d->weight_bf16x3 != nullptr;
   a.strict_release = g_tc_strict;
+  a.fmt = (a.bf16x3 && d->split_fmt == 1) ? 1 : 0;
+  a.acc_scale = (a.bf16x3 && d->acc_scale > 0.f) ? d->acc_scale : 1.f;
   a.nstack = (a.bf16x3 && d->bf16x3_nstack) ? 1 : 0;
   a.src_scale[0] = d->src_scale[0]; a.src_scale[1] = d->src_scale[1];
   a.src_affine[0] = d->src_affine[0]; a.src_affine[1] = d->src_affine[1];

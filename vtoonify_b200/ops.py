@@ -46,7 +46,7 @@ def get_precision() -> str:
 # row-strip kernel (vertical taps stacked along N, cross-row accumulation in TMEM: conv_rs.cu); rs_fmt: its operand split
 # ("bf16" | "f16": fp16 halves carry 11 + 11 mantissa bits instead of 8 + 8, weights pre-scaled by 2^10).
 _options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smalln_via_tc": True, "bf16x3_nstack": False, "fuse_adain": True,
-            "rs_conv": True, "rs_min_width": 256, "rs_fmt": "bf16", "nvtx": bool(_os.environ.get("VT_NVTX")),
+            "rs_conv": True, "rs_min_width": 256, "rs_fmt": _os.environ.get("VT_SPLIT_FMT", "bf16"), "nvtx": bool(_os.environ.get("VT_NVTX")),
             # rsu_conv: up-convolutions with Cin <= rsu_max_cin and rows of >= rs_min_width pixels on the row-strip up-conv kernel
             # (horizontal blur folded into the weights, vertical blur on the TMEM accumulators: conv_rsu.cu)
             "rsu_conv": True, "rsu_max_cin": 128}
@@ -59,14 +59,26 @@ def use_folded_upconv(cin: int) -> bool:
     return bool(v) if isinstance(v, bool) else cin <= int(v)
 
 
+_OPTION_ALIASES = {"split_fmt": "rs_fmt"}   # one split format for all three tensor-core kernels
+
+
 def set_option(name: str, value) -> None:
+    name = _OPTION_ALIASES.get(name, name)
     if name not in _options:
         raise KeyError(name)
+    if name == "rs_fmt" and value not in ("bf16", "f16"):
+        raise ValueError("split_fmt must be 'bf16' or 'f16'")
     _options[name] = value
 
 
 def get_option(name: str):
-    return _options[name]
+    return _options[_OPTION_ALIASES.get(name, name)]
+
+
+# fp16 split: weights are multiplied by this power of two before the split so that the low halves of small (demodulated,
+# 1/sqrt(fan_in)-sized) weights stay out of fp16's subnormal range; the kernels undo it on the accumulators (acc_scale).
+# |weight| must stay below 65504 / 256.
+F16_WEIGHT_SCALE = 256.0
 
 
 # Optional per-launch timing of the tensor-core convolution (bench.py's roofline leg): when set to a list, every
@@ -497,8 +509,12 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
         # measured on B200 it is no faster end to end (the epilogue's second TMEM load + add becomes the limiter: DESIGN.md
         # section 4), so it is off by default
         nstack = bool(_options["bf16x3_nstack"]) and Cout == 32 and phase_offs is None
-        d.weight_bf16x3 = split_weights_bf16x3(weight, nstack).data_ptr()
-        d.bf16x3_nstack = 1 if nstack else 0
+        if _options["rs_fmt"] == "f16" and not nstack:
+            d.weight_bf16x3 = split_weights_f16x3(weight).data_ptr()
+            d.split_fmt, d.acc_scale = 1, 1.0 / F16_WEIGHT_SCALE
+        else:
+            d.weight_bf16x3 = split_weights_bf16x3(weight, nstack).data_ptr()
+            d.bf16x3_nstack = 1 if nstack else 0
     if use_tc:
         if _tc_profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -554,14 +570,28 @@ def rs_weights(weight: torch.Tensor, fmt: str = "bf16"):
     rows = w.numel() // 32
     out = torch.empty((rows, 32), device=weight.device, dtype=torch.float32)
     if fmt == "f16":
-        scale = 1024.0
-        check(_lib.load().vt_split_weights_f16x3(w.data_ptr(), out.data_ptr(), rows, 32, scale, _stream()))
-        acc_scale = 1.0 / scale
+        check(_lib.load().vt_split_weights_f16x3(w.data_ptr(), out.data_ptr(), rows, 32, F16_WEIGHT_SCALE, _stream()))
+        acc_scale = 1.0 / F16_WEIGHT_SCALE
     else:
         check(_lib.load().vt_split_weights_bf16x3(w.data_ptr(), out.data_ptr(), rows, 32, 0, _stream()))
         acc_scale = 1.0
     weight._vt_rs = (ver, weight.data_ptr(), fmt, out, acc_scale)
     return out, acc_scale
+
+
+def split_weights_f16x3(weight: torch.Tensor) -> torch.Tensor:
+    """fp16 counterpart of :func:`split_weights_bf16x3`: chunks hold ``[half(w * 256) | half(w * 256 - hi)]``; cached on the tensor."""
+    ver = weight._version
+    cached = getattr(weight, "_vt_f16x3", None)
+    if cached is not None and cached[0] == ver and cached[1] == weight.data_ptr():
+        return cached[2]
+    if weight.shape[-1] % 32 != 0 or not weight.is_contiguous():
+        raise _lib.VtError("split_weights_f16x3: weight channel stride must be a multiple of 32")
+    rows = weight.numel() // weight.shape[-1]
+    out = torch.empty((rows, weight.shape[-1]), device=weight.device, dtype=torch.float32)
+    check(_lib.load().vt_split_weights_f16x3(weight.data_ptr(), out.data_ptr(), rows, weight.shape[-1], F16_WEIGHT_SCALE, _stream()))
+    weight._vt_f16x3 = (ver, weight.data_ptr(), out)
+    return out
 
 
 def affine_fusable(precision: Optional[str] = None) -> bool:
@@ -682,9 +712,8 @@ def conv_up2_rs_nhwc(x: torch.Tensor, w9: torch.Tensor, blur_kernel: torch.Tenso
         check(lib.vt_fold_upconv_x_weights_f32(w9.data_ptr(), garr, folded.data_ptr(), wB, Cout, Cin, _stream()))
         wsplit = torch.empty_like(folded)
         if fmt == "f16":
-            scale = 1024.0
-            check(lib.vt_split_weights_f16x3(folded.data_ptr(), wsplit.data_ptr(), n // 32, 32, scale, _stream()))
-            acc_scale = 1.0 / scale
+            check(lib.vt_split_weights_f16x3(folded.data_ptr(), wsplit.data_ptr(), n // 32, 32, F16_WEIGHT_SCALE, _stream()))
+            acc_scale = 1.0 / F16_WEIGHT_SCALE
         else:
             check(lib.vt_split_weights_bf16x3(folded.data_ptr(), wsplit.data_ptr(), n // 32, 32, 0, _stream()))
             acc_scale = 1.0

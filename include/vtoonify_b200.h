@@ -191,7 +191,8 @@ int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 a
  * and the partial sums of an output row are accumulated across input rows inside TMEM.  Same descriptor; `weight_bf16x3` must hold the
  * row-strip weight layout [wB][Cin/32][dx = -1,0,1][3*Cout rows: (dy = +1, 0, -1) x Cout][hi(32) | lo(32) 16-bit] and
  * `bf16x3_nstack` names the split format (2: bf16, 3: fp16).  Epilogue: v = acc * acc_scale + bias + noise_w * noise -> activation
- * (-> fused ToRGB tail).  Dense NHWC output only. */
+ * (-> fused ToRGB tail).  Dense NHWC output only.  With the ToRGB tail present `out` may be NULL: only `rgb_out` is written (the
+ * last StyledConv of the synthesis network: its activation has no reader, model/stylegan/model.py:549-556). */
 int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream);
 int vt_conv2d_rs_supported(const vt_conv_desc* d);
 /* Row-strip UP-convolution (StyledConv up-layers, model/stylegan/model.py:273-286): out = Blur4x4(conv_transpose2d(in, w, stride 2)),

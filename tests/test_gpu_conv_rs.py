@@ -100,6 +100,14 @@ def test_rs_fused_torgb(rs_knobs, cg, Cin, H, W, B, wB):
     _, r0 = _run(x, w, kw, H, W, rs=False, rgb=rgb2)
     _, r1 = _run(x, w, kw, H, W, rs=True, rgb=rgb2)
     assert (r0 - r1).abs().max().item() <= 6e-5 * r0.abs().max().item()
+    # RGB-only launch (the generator's last layer): no activation is written, the image is bit-identical; the tap-by-tap route
+    # ignores the hint and still returns the activation
+    for r in (rgb, rgb2):
+        none_out, only = _run(x, w, kw, H, W, rs=True, rgb=dict(r, only=True))
+        full_out, full = _run(x, w, kw, H, W, rs=True, rgb=r)
+        assert none_out is None and torch.equal(only, full)
+    o2, r2 = _run(x, w, kw, H, W, rs=False, rgb=dict(rgb, only=True))
+    assert o2 is not None and torch.equal(o2, ref) and torch.equal(r2, ref_rgb)
 
 
 def test_rs_default_routing():

@@ -32,7 +32,8 @@ with torch.no_grad():
         pl = torch.randn((B, 3, H, W), device=dev); wpl = torch.randn((9, 3, 3), device=dev)
         mask = lambda: ops.smalln_conv(x, w1, ops.conv_taps(3, 1), 1, B, H, W, bias=b1, act=_lib.ACT_RELU_TANH, mul_src=fe, src2=x2, tap_const=kc)
         skip = lambda: ops.smalln_conv(fe, w3, ops.conv_taps(3, 1), 3, B, H, W, planar=pl, planar_weight=wpl)
-        for name, fn, nbytes in (("mask  N=1 [x||x-x2|] + f_E*m", mask, 4.0 * B * H * W * C * 4), ("skip  N=3 + planar", skip, 4.0 * B * H * W * C)):
+        mask_p = lambda: ops.smalln_conv(x, w1, ops.conv_taps(3, 1), 1, B, H, W, bias=b1, act=_lib.ACT_RELU_TANH, src2=x2, tap_const=kc)
+        for name, fn, nbytes in (("mask  N=1 [x||x-x2|] (product)", mask_p, 4.0 * B * H * W * C * 2), ("mask  N=1 [x||x-x2|] + f_E*m", mask, 4.0 * B * H * W * C * 4), ("skip  N=3 + planar", skip, 4.0 * B * H * W * C)):
             res = []
             for mode in (0, 2):
                 old = lib.vt_set_option(b"smalln_is", mode)

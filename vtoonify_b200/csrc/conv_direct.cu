@@ -453,13 +453,24 @@ smalln_is_kernel(const __grid_constant__ SmallNArgs args, int dy0, int dy1, int 
       for (int it = 0; it < IT; ++it)
 #pragma unroll
         for (int tn = 0; tn < TN; ++tn) acc[it][tn] = 0.f;
-      for (int c = sub * 4; c < d.src_c; c += 32) {
-        float4 a[IT], e[IT];
+      // software pipeline without extra registers: a's registers are dead after the |a - e| step, so the next trip's a is
+      // requested there (covered by the e-half of the math), and the next e right after the e-half (covered by the next a-half).
+      // The kernel is latency-bound (2 blocks x 8 warps per SM at 128 registers), not FMA-bound.
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a[IT], e[IT];
+      {
+        const int c0 = sub * 4;
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
-          a[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(pa[it] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (d.src_mask) { a[it].x *= pm[it]; a[it].y *= pm[it]; a[it].z *= pm[it]; a[it].w *= pm[it]; }
-          if (d.src2_mode) e[it] = ok[it] ? __ldg(reinterpret_cast<const float4*>(pe[it] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          a[it] = (ok[it] && c0 < d.src_c) ? __ldg(reinterpret_cast<const float4*>(pa[it] + c0)) : z4;
+          e[it] = (d.src2_mode && ok[it] && c0 < d.src_c) ? __ldg(reinterpret_cast<const float4*>(pe[it] + c0)) : z4;
+        }
+      }
+      for (int c = sub * 4; c < d.src_c; c += 32) {
+        const int cn = c + 32;
+        if (d.src_mask) {
+#pragma unroll
+          for (int it = 0; it < IT; ++it) { a[it].x *= pm[it]; a[it].y *= pm[it]; a[it].z *= pm[it]; a[it].w *= pm[it]; }
         }
 #pragma unroll
         for (int tn = 0; tn < TN; ++tn) {
@@ -478,6 +489,11 @@ smalln_is_kernel(const __grid_constant__ SmallNArgs args, int dy0, int dy1, int 
             e[it].x = fabsf(a[it].x - e[it].x); e[it].y = fabsf(a[it].y - e[it].y);
             e[it].z = fabsf(a[it].z - e[it].z); e[it].w = fabsf(a[it].w - e[it].w);
           }
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+          a[it] = (ok[it] && cn < d.src_c) ? __ldg(reinterpret_cast<const float4*>(pa[it] + cn)) : z4;
+        if (d.src2_mode) {
 #pragma unroll
           for (int tn = 0; tn < TN; ++tn) {
             const float4 w = *reinterpret_cast<const float4*>(Ws + (size_t)tn * CW + d.src_c + c);
@@ -489,6 +505,9 @@ smalln_is_kernel(const __grid_constant__ SmallNArgs args, int dy0, int dy1, int 
               acc[it][tn] = fmaf(e[it].w, w.w, acc[it][tn]);
             }
           }
+#pragma unroll
+          for (int it = 0; it < IT; ++it)
+            e[it] = (ok[it] && cn < d.src_c) ? __ldg(reinterpret_cast<const float4*>(pe[it] + cn)) : z4;
         }
       }
       // reduce over the 8 channel-slice lanes; lane (tn & 7) of the pixel's group stores entry tn
@@ -653,14 +672,18 @@ extern "C" int vt_smalln_conv_f32(const vt_smalln_desc* d, void* stream) {
     const int RH = IS_PH + dy1 - dy0, RW = IS_PW + dx1 - dx0;
     const size_t smem_is = ((size_t)tn * (cw + d->n_planar) + 16 + ((tn + 3) & ~3) + (size_t)RH * RW * TS) * sizeof(float);
     if (dy1 - dy0 <= 4 && dx1 - dx0 <= 4 && smem_is <= 200 * 1024) {
-      int64_t blocks = vt_cdiv(d->W, IS_PW) * vt_cdiv(d->H, IS_PH);
-      const int64_t cap = vt_cdiv((int64_t)vt_num_sms() * 3, d->B);
-      if (blocks > cap) blocks = cap;
-      dim3 grid((unsigned)blocks, (unsigned)d->B);
+      const int64_t patches = vt_cdiv(d->W, IS_PW) * vt_cdiv(d->H, IS_PH);
+      // persistent over patches: exactly one wave of resident blocks (a 1.5-wave grid ran its second half on half the slots)
 #define VT_LAUNCH_IS(NN, ITT)                                                                                          \
   do {                                                                                                                 \
     if (smem_is > 48 * 1024)                                                                                           \
       VT_CUDA(cudaFuncSetAttribute(smalln_is_kernel<NN, ITT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_is)); \
+    int occ = 0;                                                                                                       \
+    VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smalln_is_kernel<NN, ITT>, 256, smem_is));             \
+    int64_t blocks = ((int64_t)vt_num_sms() * (occ > 0 ? occ : 1)) / d->B;                                             \
+    if (blocks < 1) blocks = 1;                                                                                        \
+    if (blocks > patches) blocks = patches;                                                                            \
+    dim3 grid((unsigned)blocks, (unsigned)d->B);                                                                       \
     smalln_is_kernel<NN, ITT><<<grid, 256, smem_is, st>>>(a, dy0, dy1, dx0, dx1, TS);                                    \
   } while (0)
       switch (d->Cout) {

@@ -58,6 +58,7 @@ struct RsArgs {
   int fmt;                 // operand split: 0 = bf16 hi/lo, 1 = fp16 hi/lo
   float acc_scale;         // accumulators are multiplied by this before the bias (undoes a power-of-two weight scale)
   int strict_release;      // 1: cluster-scope release on the transform warps' remote arrive (A/B switch for tests)
+  int store_out;           // 0: only the fused ToRGB image is produced (last layer of the generator: the activation has no reader)
   unsigned long long* dbg;
 };
 
@@ -122,7 +123,8 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
   const bool is_xform = warp == 2 || warp == 3 || warp >= 12;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.in_map); tma_prefetch_desc(&p.w_map); tma_prefetch_desc(&p.out_map);
+    tma_prefetch_desc(&p.in_map); tma_prefetch_desc(&p.w_map);
+    if (p.store_out) tma_prefetch_desc(&p.out_map);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_ready(i), RS_XFORM_WARPS * CG); mbar_init(a_empty(i), 1); }
@@ -450,6 +452,7 @@ conv_rs_kernel(const __grid_constant__ RsArgs p) {
           }
           const long long t_e2 = timed ? clock64() : 0;
           if (timed) tw[2] += t_e2 - t_e1;
+          if (!p.store_out) continue;
           // per-warp staging (32 pixels x 128 B, 128B-swizzled) + per-warp TMA store: no CTA-wide barrier in the epilogue
           const uint32_t sbuf = sbuf0 + (n_store & 1u) * 4096u;
           if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer two stores ago has read it
@@ -531,7 +534,8 @@ int rs_check(const vt_conv_desc* d, bool set_err) {
   RS_SUP(d->weight_bf16x3 != nullptr && (d->bf16x3_nstack == 2 || d->bf16x3_nstack == 3),
          "conv_rs: weight_bf16x3 must hold the row-strip layout (bf16x3_nstack = 2: bf16 split, 3: fp16 split)");
   RS_SUP(d->wB == 1 || d->wB == d->B, "conv_rs: wB must be 1 or B");
-  RS_SUP(d->out_sx == d->Cout && d->out_sy == (int64_t)d->Wo * d->Cout && d->out_sb == (int64_t)d->Ho * d->Wo * d->Cout && d->phase_off[0] == 0,
+  RS_SUP(d->out != nullptr || (d->rgb_w != nullptr && d->rgb_out != nullptr), "conv_rs: out may be NULL only with the fused ToRGB tail (RGB-only launch)");
+  RS_SUP(d->out == nullptr || (d->out_sx == d->Cout && d->out_sy == (int64_t)d->Wo * d->Cout && d->out_sb == (int64_t)d->Ho * d->Wo * d->Cout && d->phase_off[0] == 0),
          "conv_rs: dense NHWC output only");
   RS_SUP(!d->res && !d->slope_vec && !d->src_scale[0] && !d->src_affine[0] && !d->round_tf32, "conv_rs: no residual / PReLU / source transforms / TF32 rounding");
   RS_SUP(d->act == VT_ACT_NONE || d->act == VT_ACT_LRELU, "conv_rs: activation must be none or leaky-relu");
@@ -624,7 +628,8 @@ extern "C" int vt_conv2d_rs(const vt_conv_desc* d, float acc_scale, void* stream
     const uint32_t box[4] = {64, (uint32_t)(3 * Cout / cg), 1, 1};
     if (vt_tc_make_map4(&a.w_map, d->weight_bf16x3, dims, str, box, "rs weight", true)) return 1;
   }
-  {
+  a.store_out = d->out != nullptr;
+  if (a.store_out) {
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     const uint64_t str[3] = {(uint64_t)Cout * 4, (uint64_t)d->W * Cout * 4, (uint64_t)d->H * d->W * Cout * 4};
     const uint32_t box[4] = {32, 32, 1, 1};

@@ -33,7 +33,30 @@ instnorm_partial_kernel(const float* __restrict__ in, const float* __restrict__ 
   const int v = threadIdx.x % nvec, lane_p = threadIdx.x / nvec;
   if (lane_p < pstep) {
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
-    for (int64_t p = p_begin + lane_p; p < p_end; p += pstep) {
+    // four pixels per trip: the loads are issued together (the kernel is latency-bound: one 16-byte load in flight per thread
+    // gave 1.2 TB/s on L2-resident maps), the accumulation order stays the pixel order
+    int64_t p = p_begin + lane_p;
+    for (; p + 3 * (int64_t)pstep < p_end; p += 4 * (int64_t)pstep) {
+      float4 a[4], e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = __ldg(reinterpret_cast<const float4*>(ip + (p + u * (int64_t)pstep) * c_stride + v * 4));
+      if (mode) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = __ldg(reinterpret_cast<const float4*>(ip2 + (p + u * (int64_t)pstep) * c_stride + v * 4));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float av[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[i] += av[i]; q[i] = fmaf(av[i], av[i], q[i]); }
+        if (mode) {
+          const float ev[4] = {e[u].x, e[u].y, e[u].z, e[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float d = fabsf(av[i] - ev[i]); s2[i] += d; q2[i] = fmaf(d, d, q2[i]); }
+        }
+      }
+    }
+    for (; p < p_end; p += pstep) {
       const float4 a = *reinterpret_cast<const float4*>(ip + p * c_stride + v * 4);
       const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -283,8 +306,8 @@ fir4_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
 static void instnorm_plan(int64_t HW, int C, int64_t* chunk, int64_t* chunks) {
   const int nvec = C / 4;
   const int plan = 256 / nvec;                      // pixels processed concurrently by a block
-  int64_t ch = (int64_t)plan * 128;                 // ~128 pixels per thread
-  if (ch < 256) ch = 256;
+  int64_t ch = (int64_t)plan * 32;                  // 32 pixels per thread: several blocks per SM even on the 72x128 maps
+  if (ch < 64) ch = 64;
   *chunk = ch;
   *chunks = vt_cdiv(HW, ch);
 }

@@ -422,16 +422,21 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
     d.n_phase = 1 if phase_offs is None else len(phase_offs)
     d.weight = weight.data_ptr()
     d.wB, d.w_taps, d.w_cstride, d.Cout = wB, w_taps, w_cs, Cout
+    # rgb["only"]: the caller has no use for the activation (last generator layer) -> a kernel that supports it gets out = NULL
+    # and only produces the image; every other route allocates the activation as usual and drops it on return
+    rgb_only = rgb is not None and bool(rgb.get("only")) and out is None and out_view is None
     if out is None:
-        out = torch.empty((B, Ho, Wo, Cout), device=srcs[0].device, dtype=torch.float32)
-    if out_view is None:
+        out = torch.empty((B, Ho, Wo, Cout), device=srcs[0].device, dtype=torch.float32) if not rgb_only else None
+    if rgb_only:
+        off, sb, sy, sx = 0, Ho * Wo * Cout, Wo * Cout, Cout
+    elif out_view is None:
         off, sb, sy, sx = 0, Ho * Wo * Cout, Wo * Cout, Cout
         if out.shape != (B, Ho, Wo, Cout) or not out.is_contiguous():
             raise _lib.VtError("conv2d_nhwc: bad out tensor")
     else:
         off, sb, sy, sx = out_view
-    d.out = out.data_ptr()
-    d.out_cpitch = out.shape[-1]
+    d.out = out.data_ptr() if out is not None else None
+    d.out_cpitch = out.shape[-1] if out is not None else Cout
     if phase_offs is None:
         d.phase_off[0] = off
     else:
@@ -490,16 +495,19 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 cin = int(d.src_c[0])
                 flops = 2.0 * B * Ho * Wo * Cout * cin * 9
-                nbytes = 4.0 * (B * H * W * cin + B * Ho * Wo * Cout + weight.numel())
+                nbytes = 4.0 * (B * H * W * cin + B * Ho * Wo * (Cout if out is not None else 3) + weight.numel())
                 e0.record()
                 check(lib.vt_conv2d_rs(d, acc_scale, _stream()))
                 e1.record()
-                _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout} k9 s1 {H}x{W} [row-strip]", 3.0 * flops))
+                _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout} k9 s1 {H}x{W} [row-strip{'' if out is not None else ', image only'}]", 3.0 * flops))
             else:
                 check(lib.vt_conv2d_rs(d, acc_scale, _stream()))
             return out if rgb is None else (out, rgb_out)
         d.weight_bf16x3 = None
         d.bf16x3_nstack = 0
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), device=srcs[0].device, dtype=torch.float32)
+        d.out = out.data_ptr()
     if prec == "bf16x3":
         d.weight_bf16x3 = weight.data_ptr()   # marks the mode for vt_conv2d_tc_supported; the split buffer is attached below
     use_tc = prec in ("tf32", "bf16x3") and lib.vt_conv2d_tc_supported(d)

@@ -289,9 +289,11 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward_nhwc(self, x, style, noise=None, externalweight=None, zero_noise=False, to_rgb=None):
+    def forward_nhwc(self, x, style, noise=None, externalweight=None, zero_noise=False, to_rgb=None, rgb_only=False):
         """``to_rgb`` = (ToRGB module, its style, skip image or None): also returns the RGB image, computed in this
-        conv's epilogue when possible (the activation is then never re-read for the 1x1 ToRGB conv)."""
+        conv's epilogue when possible (the activation is then never re-read for the 1x1 ToRGB conv).  ``rgb_only``: the
+        caller drops the activation (last layer of the synthesis network): the returned ``out`` may be ``None`` and a fused
+        launch does not write it to HBM at all."""
         B, H, W, _ = x.shape
         Ho, Wo = (2 * H, 2 * W) if self.conv.upsample else (H, W)
         if zero_noise:
@@ -312,7 +314,7 @@ class StyledConv(nn.Module):
             return out, trgb.forward_nhwc(out, style_rgb, skip)
         w_rgb = trgb.conv.modulated_weights(style_rgb, Cout, round_tf32=False)      # [B, 1, 3, Cout]
         rgb = {"w": w_rgb, "bias": trgb.bias.view(3), "skip": skip,
-               "kernel": trgb.upsample.kernel if skip is not None else None}
+               "kernel": trgb.upsample.kernel if skip is not None else None, "only": rgb_only}
         return self.conv.forward_nhwc(x, style, externalweight, rgb=rgb, **kw)
 
     def forward(self, input, style, noise=None, externalweight=None):
@@ -444,10 +446,12 @@ class Generator(ops.WeightsEpochMixin, nn.Module):
         out = self.conv1.forward_nhwc(out, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1.forward_nhwc(out, latent[:, 1])
         i = 1
-        for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
-                                                        self.to_rgbs):
+        n_levels = len(self.to_rgbs)
+        for lvl, (conv1, conv2, noise1, noise2, to_rgb) in enumerate(zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
+                                                                         self.to_rgbs)):
             out = conv1.forward_nhwc(out, latent[:, i], noise=noise1)
-            out, skip = conv2.forward_nhwc(out, latent[:, i + 1], noise=noise2, to_rgb=(to_rgb, latent[:, i + 2], skip))
+            last = lvl == n_levels - 1 and i + 2 <= return_feature_ind     # nobody reads the last activation (model.py:549-556)
+            out, skip = conv2.forward_nhwc(out, latent[:, i + 1], noise=noise2, to_rgb=(to_rgb, latent[:, i + 2], skip), rgb_only=last)
             i += 2
             if i > return_feature_ind:
                 return ops.nhwc_as_nchw_view(out), skip

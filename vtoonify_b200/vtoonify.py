@@ -276,7 +276,8 @@ class VToonify(ops.WeightsEpochMixin, nn.Module):
         G = self.stylegan()
         _index = 1
         m_Es = []
-        for conv1, conv2, to_rgb in zip(G.convs[6::2], G.convs[7::2], G.to_rgbs[3:]):
+        levels = list(zip(G.convs[6::2], G.convs[7::2], G.to_rgbs[3:]))
+        for lvl, (conv1, conv2, to_rgb) in enumerate(levels):
             if 2 ** (5 + ((_index - 1) // 2)) <= self.in_size:
                 fi = (_index - 1) // 2
                 f_E = encoder_features[fi]
@@ -293,8 +294,9 @@ class VToonify(ops.WeightsEpochMixin, nn.Module):
                         skip = self.fusion_skip[fi].forward_smalln(f_E, planar=skip)
             with ops.nvtx_range(f"vtoonify/generator.level{(_index - 1) // 2}"):
                 out = conv1.forward_nhwc(out, adastyles[:, _index + 6], zero_noise=True)
+                # the activation of the last level has no reader (model/vtoonify.py:273-284): only its image is produced
                 out, skip = conv2.forward_nhwc(out, adastyles[:, _index + 7], zero_noise=True,
-                                               to_rgb=(to_rgb, adastyles[:, _index + 8], skip))
+                                               to_rgb=(to_rgb, adastyles[:, _index + 8], skip), rgb_only=lvl == len(levels) - 1)
             _index += 2
 
         image = skip

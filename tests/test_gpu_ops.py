@@ -227,7 +227,7 @@ def test_upfirdn2d_tiled_and_generic_kernels_agree():
         k = torch.randn((kh, kw), generator=g)
         ref = O.upfirdn2d(x, k, up, down, pad)
         outs = []
-        for tiled in (1, 0):
+        for tiled in (2, 1, 0):
             old = lib.vt_set_option(b"upfirdn_tiled", tiled)
             try:
                 outs.append(upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad).cpu())
@@ -237,6 +237,53 @@ def test_upfirdn2d_tiled_and_generic_kernels_agree():
             assert y.shape == ref.shape, (H, W, kh, kw, up, down, pad)
             assert maxerr(y, ref) <= 2e-5 * max(1.0, ref.abs().max().item()), (H, W, kh, kw, up, down, pad, maxerr(y, ref))
         n += 1
+
+
+@pytest.mark.parametrize("up,down", [(1, 1), (2, 1), (1, 2)])
+def test_upfirdn2d_streaming_kernel(up, down):
+    """The streaming 4x4 kernel (bulk-copy ring + register column filters; default for Blur / Upsample / Downsample) against the
+    oracle and the generic kernel: strips (> 256 / 512 output columns), row chunks, ring laps, rows of 4k+1..4k+3 floats (every
+    copy lead), pads 0..5 and crops, separable and full-rank taps, 1-pixel planes, a view that starts 4 bytes into its storage."""
+    from vtoonify_b200 import _lib
+    from vtoonify_b200.op import upfirdn2d
+    lib = _lib.load()
+    assert lib.vt_set_option(b"upfirdn_tiled", 2) == 2       # it is the default
+    g = torch.Generator().manual_seed(100 * up + down)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    ksep = k1[:, None] * k1[None, :] / 64 * (up * up)
+    cases = [(1, 3, 70, 300), (2, 2, 33, 1025), (1, 1, 1, 1), (1, 2, 5, 3), (3, 1, 129, 515), (1, 1, 200, 64), (2, 1, 16, 2050)]
+    pads = [(1, 1), (2, 1), (2, 2), (0, 0), (3, 0), (5, 4), (-1, 2), (1, -1)]
+    n = 0
+    for ci, (B, C, H, W) in enumerate(cases):
+        for pi, pad in enumerate(pads):
+            if (ci + pi) % 3 and ci > 1:
+                continue                                   # every case with a third of the pads (all pads on the first two)
+            oh = (H * up + pad[0] + pad[1] - 4 + down) // down
+            ow = (W * up + pad[0] + pad[1] - 4 + down) // down
+            if oh < 1 or ow < 1 or H * up + min(pad[0], 0) + min(pad[1], 0) < 1 or W * up + min(pad[0], 0) + min(pad[1], 0) < 1:
+                continue
+            for sep in (True, False):
+                k = ksep if sep else torch.randn((4, 4), generator=g)
+                x = torch.randn((B, C, H, W), generator=g)
+                ref = O.upfirdn2d(x, k, up, down, pad)
+                y = upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad).cpu()
+                old = lib.vt_set_option(b"upfirdn_tiled", 0)
+                try:
+                    y0 = upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad).cpu()
+                finally:
+                    lib.vt_set_option(b"upfirdn_tiled", old)
+                tol = 2e-6 * max(1.0, ref.abs().max().item())
+                assert y.shape == ref.shape
+                assert maxerr(y, ref) <= tol and maxerr(y, y0) <= tol, (B, C, H, W, pad, sep, maxerr(y, ref), maxerr(y, y0))
+                n += 1
+    # misaligned storage: the tensor starts 4 / 8 / 12 bytes into its allocation (first / last rows take the in-bounds path)
+    for off in (1, 2, 3):
+        buf = torch.randn(2 * 3 * 37 * 131 + off, generator=g).cuda()
+        x = buf[off:].view(2, 3, 37, 131)
+        assert x.data_ptr() % 16 == 4 * off
+        ref = O.upfirdn2d(x.cpu(), ksep, up, down, (2, 1))
+        assert maxerr(upfirdn2d(x, ksep.cuda(), up=up, down=down, pad=(2, 1)).cpu(), ref) <= 2e-6 * max(1.0, ref.abs().max().item())
+    assert n >= 40
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 33, 65), (1, 64, 17, 130), (1, 8, 9, 7)])

@@ -14,7 +14,7 @@ def t(fn, reps=10):
 x = torch.randn((8, 32, 1025, 1025), device="cuda")          # BASELINE configs[2]: blur [8,32,1025,1025]
 s = torch.randn((8, 3, 512, 512), device="cuda")
 from vtoonify_b200 import _lib
-for sep in (1, 0):
+for sep in (2, 1, 0):
     _lib.load().vt_set_option(b"upfirdn_tiled", sep)
     ms = t(lambda: upfirdn2d(x, k, pad=(1, 1)))
     gb = (x.numel() + 8 * 32 * 1024 * 1024) * 4 / 1e9

@@ -586,7 +586,8 @@ static int validate_conv_desc(const vt_conv_desc* d, const char* who) {
   VT_CHECK(d->n_src == 1 || d->n_src == 2, "%s: n_src must be 1 or 2", who);
   VT_CHECK(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Ho >= 1 && d->Wo >= 1, "%s: bad spatial shape", who);
   VT_CHECK(d->stride >= 1 && d->taps >= 1 && d->taps <= VT_MAX_TAPS, "%s: bad stride/taps", who);
-  VT_CHECK(d->Cout >= 1 && d->weight && d->out, "%s: bad weight/out", who);
+  // out == NULL is the "image only" form of the fused ToRGB tail (row-strip kernel; the others reject it below)
+  VT_CHECK(d->Cout >= 1 && d->weight && (d->out || (d->rgb_w && d->rgb_out)), "%s: bad weight/out", who);
   VT_CHECK(d->wB == 1 || d->wB == d->B, "%s: wB must be 1 or B", who);
   int ctot = 0;
   for (int s = 0; s < d->n_src; ++s) {
@@ -613,7 +614,7 @@ int vt_validate_conv_desc(const vt_conv_desc* d, const char* who) { return valid
 extern "C" int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream) {
   if (validate_conv_desc(d, "conv2d_direct")) return 1;
   VT_CHECK(d->B <= 65535 && vt_cdiv(d->Cout, BN) <= 65535, "conv2d_direct: grid too large");
-  VT_CHECK(!d->rgb_w, "conv2d_direct: the fused ToRGB tail exists only in the tensor-core kernel");
+  VT_CHECK(!d->rgb_w && d->out, "conv2d_direct: the fused ToRGB tail exists only in the tensor-core kernel");
   VT_CHECK(!d->src_scale[0] && !d->src_scale[1] && !d->src_affine[0] && !d->src_affine[1],
            "conv2d_direct: src_scale / src_affine are only implemented by the bf16x3 tensor-core kernel");
   const int64_t HoWo = (int64_t)d->Ho * d->Wo;

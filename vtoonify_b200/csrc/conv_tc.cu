@@ -689,6 +689,7 @@ int g_tc_strict = 1;  // 1: cluster-scope release arrive in the transform warps 
 int check_supported(const vt_conv_desc* d, bool set_err) {
 #define VT_SUP(cond, ...) do { if (!(cond)) { if (set_err) vt_set_error(__VA_ARGS__); return 0; } } while (0)
   VT_SUP(d->Cout % 32 == 0, "conv_tc: Cout must be a multiple of 32 (got %d)", d->Cout);
+  VT_SUP(d->out != nullptr, "conv_tc: out must not be NULL (the image-only ToRGB form exists in the row-strip kernel only)");
   for (int s = 0; s < d->n_src; ++s) {
     VT_SUP(d->src_c[s] % KCH == 0, "conv_tc: src_c[%d]=%d must be a multiple of 32", s, d->src_c[s]);
     VT_SUP(d->src_cstride[s] % 4 == 0, "conv_tc: channel stride must be a multiple of 4");

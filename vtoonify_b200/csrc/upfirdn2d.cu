@@ -11,9 +11,11 @@
 //   * upfirdn2d_generic_kernel : any (up, down, pad, kh, kw); one output per thread.
 //   * upfirdn2d_tiled_kernel   : same semantics, the input window of a 32 x 64 output tile staged once in shared memory
 //     (coalesced), division-free tap loops; used whenever the window fits (all hot-path instances).
-#include "common.cuh"
+#include "tc_common.cuh"
 
-int g_upfirdn_tiled = 1;   // 0 forces the generic kernel (tests compare both)
+using namespace vt_tc;
+
+int g_upfirdn_tiled = 2;   // 2: streaming kernel for the 4x4 instances (default); 1: staged-tile kernels; 0 forces the generic kernel (tests compare all)
 
 namespace {
 
@@ -237,6 +239,463 @@ int launch_k4(const float* in, const float* kernel, float* out, int64_t planes, 
   return 0;
 }
 
+
+// ---- streaming 4x4 kernel (default for the StyleGAN instances: Blur, Upsample x2, Downsample /2) ---------------------------
+// The k4 kernel above stages a tile with per-lane 4-byte loads, waits, computes, stores: at most ~20 KB in flight per SM and
+// 0.35 of the HBM roof.  Here a block walks a column strip of one plane from top to bottom:
+//   * a producer warp streams the input rows of the strip into a shared-memory ring with 1-D bulk async copies
+//     (cp.async.bulk, completion on an mbarrier; lane rr issues row rr of a stage): a row segment is contiguous in a planar
+//     tensor, so no tensor map (and no 16-byte row pitch, which [.., 1025, 1025] planes do not have) is needed - the copy
+//     starts at the 16-byte boundary below the segment and the consumers add the row's 0..3-float lead to their column
+//     index.  ~68 KB are in flight per block, no registers or LSU slots are spent on the loads.  Rows in the zero padding
+//     are written as zeros by the producer warp; a copy that would touch bytes outside the tensor (only the first / last
+//     row of the whole tensor) is done with ordinary predicated loads instead.
+//   * the consumer threads keep the vertical taps' partial sums in registers while the rows stream by, so every input
+//     element comes from HBM once.  Blur and Upsample: a thread owns 4 (8) adjacent output columns, reads its 7 (6) inputs of
+//     a row as three aligned 16-byte shared loads (the row's lead decides which of the 12 registers are used - a uniform
+//     4-way branch) and stores 16 bytes per output row: 13 (6) instructions per output instead of 44 (the first, one
+//     column per thread version was issue-bound at 0.46 of the HBM roof).  A rank-1 blur kernel (every StyleGAN filter:
+//     outer([1,3,3,1])) is applied separably: 4 FMAs for the row filter + 4 for the column filter per output instead of 16.
+//     Downsample: one output column per thread (4 scalar loads per input row, 2 input rows per output).
+// Output rows go straight from registers to global memory (consecutive lanes -> consecutive 16-byte / 4-byte pieces).
+constexpr int US_RS = 8;                   // input rows per ring stage
+constexpr int US_STAGES = 4;
+
+template <int UP, int DOWN> struct UsCfg;
+template <> struct UsCfg<1, 1> { static constexpr int NCONS = 128, OWT = 512, COUNT = 515; };    // 4 output columns per thread
+template <> struct UsCfg<2, 1> { static constexpr int NCONS = 128, OWT = 1024, COUNT = 514; };   // 8 output columns (4 inputs) per thread
+template <> struct UsCfg<1, 2> { static constexpr int NCONS = 256, OWT = 256, COUNT = 514; };    // 1 output column per thread
+
+struct UsArgs {
+  const float* in; const float* kernel; float* out;
+  int64_t planes, total_items;
+  int in_h, in_w, out_h, out_w, pad_x0, pad_y0;
+  int strips, chunks, rows_per_chunk;
+  int row_stride;                          // ring: US_STAGES x US_RS rows x row_stride floats
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// geometry of a work item (plane, row chunk, column strip): identical arithmetic in the producer and the consumers
+template <int UP, int DOWN>
+struct UsItem {
+  int64_t plane;
+  int oy_a, oy_b, ox0;       // output rows [oy_a, oy_b), first output column
+  int iy_first, n_rows;      // input rows streamed: iy_first .. iy_first + n_rows - 1 (may lie in the padding)
+  int ix0;                   // input column of ring column offset 0 (may be negative)
+  int ix_lo, n_cols;         // columns actually copied: [ix_lo, ix_lo + n_cols) inside [0, in_w)
+  int colbase;               // ring column of input column ix0 (before the per-row lead)
+  __device__ __forceinline__ UsItem(const UsArgs& p, int64_t item) {
+    using C = UsCfg<UP, DOWN>;
+    const int strip = (int)(item % p.strips);
+    const int64_t t = item / p.strips;
+    const int chunk = (int)(t % p.chunks);
+    plane = t / p.chunks;
+    oy_a = chunk * p.rows_per_chunk;
+    oy_b = min(oy_a + p.rows_per_chunk, p.out_h);
+    ox0 = strip * C::OWT;
+    if (UP == 1) {
+      iy_first = oy_a * DOWN - p.pad_y0;
+      n_rows = (oy_b - 1 - oy_a) * DOWN + 4;
+      ix0 = ox0 * DOWN - p.pad_x0;
+    } else {
+      const int ty_a = oy_a - p.pad_y0, ty_l = oy_b - 1 - p.pad_y0;
+      iy_first = (ty_a + (ty_a & 1)) >> 1;
+      n_rows = ((ty_l + (ty_l & 1)) >> 1) + 1 - iy_first + 1;
+      const int tx0 = ox0 - p.pad_x0;
+      ix0 = (tx0 + (tx0 & 1)) >> 1;
+    }
+    ix_lo = max(ix0, 0);
+    n_cols = min(ix0 + C::COUNT, p.in_w) - ix_lo;
+    colbase = ((ix_lo - ix0 + 3) & ~3) - (ix_lo - ix0);   // D + (ix0 - ix_lo) with D = roundup(ix_lo - ix0, 4)
+  }
+};
+
+// ---- Blur (UP = DOWN = 1), one input row, 4 adjacent output columns per thread.  u = three aligned float4 of the ring row, the
+// thread's 7 inputs are u[SH .. SH + 6].  Input row r feeds the four output rows r - ky; the accumulator of an output row starts
+// with its first tap (ky = 0: a multiply, no clearing needed) and is stored after its last (ky = 3).
+template <bool SEP, int RR, int SH>
+__device__ __forceinline__ void us_blur_row4(const float4* sp4, unsigned mbits, const float (&kf)[16], const float (&ay)[4],
+                                             const float (&bx)[4], float (&acc)[4][4]) {
+  float u[12];
+  {
+    const float4 a = sp4[0], b = sp4[1];
+    u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
+    if (SH >= 2) { const float4 c = sp4[2]; u[8] = c.x; u[9] = c.y; u[10] = c.z; u[11] = c.w; }
+  }
+  float v[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) v[i] = ((mbits >> i) & 1u) ? u[SH + i] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (SEP) {
+      float h = bx[0] * v[c];
+      h = fmaf(bx[1], v[c + 1], h); h = fmaf(bx[2], v[c + 2], h); h = fmaf(bx[3], v[c + 3], h);
+      acc[c][RR & 3] = ay[0] * h;
+#pragma unroll
+      for (int ky = 1; ky < 4; ++ky) acc[c][(RR - ky) & 3] = fmaf(ay[ky], h, acc[c][(RR - ky) & 3]);
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        float a = ky ? acc[c][(RR - ky) & 3] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a = fmaf(kf[ky * 4 + i], v[c + i], a);
+        acc[c][(RR - ky) & 3] = a;
+      }
+    }
+  }
+}
+
+// ---- Upsample (UP = 2), one input row (the second of the two an output row needs), 8 adjacent output columns per thread.
+// The thread's inputs are u[SH .. SH + 5] (cv) and the same columns of the previous row (pv).  Output column n of the thread:
+// parity q = (tx0 + n) & 1, first input column f = (n + 1 - Q0) >> 1 (Q0 = tx0 & 1, the same for every thread of the launch).
+// y[e][n]: e = 0 -> output row 2*iy - 3 + pad (taps ky = 1, 3), e = 1 -> the next one (ky = 0, 2);  w[e][q] = {kf[kyf][q], kf[kyf][q+2],
+// kf[kys][q], kf[kys][q+2]}.
+template <int Q0, int SH>
+__device__ __forceinline__ void us_up_row8(const float4* sp4, unsigned mbits, const float (&w)[2][2][4], float (&pv)[6], float (&y)[2][8]) {
+  float u[12];
+  {
+    const float4 a = sp4[0], b = sp4[1];
+    u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
+    if (SH >= 3) { const float4 c = sp4[2]; u[8] = c.x; u[9] = c.y; u[10] = c.z; u[11] = c.w; }
+  }
+  float cv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cv[i] = ((mbits >> i) & 1u) ? u[SH + i] : 0.f;
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int q = (Q0 + n) & 1, f = (n + 1 - Q0) >> 1;
+      float t = w[e][q][0] * pv[f];
+      t = fmaf(w[e][q][1], pv[f + 1], t); t = fmaf(w[e][q][2], cv[f], t); t = fmaf(w[e][q][3], cv[f + 1], t);
+      y[e][n] = t;
+    }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) pv[i] = cv[i];
+}
+
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(UsCfg<UP, DOWN>::NCONS + 32)
+upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
+  using C = UsCfg<UP, DOWN>;
+  constexpr int NCONS = C::NCONS;
+  extern __shared__ __align__(128) float ring[];
+  __shared__ __align__(8) uint64_t bars[2 * US_STAGES];
+  __shared__ float sk[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return bar0 + (uint32_t)(US_STAGES + s) * 8u; };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < US_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NCONS / 32); }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 16) sk[threadIdx.x] = p.kernel[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)];   // flipped: true convolution
+  __syncthreads();
+  const int64_t plane_elems = (int64_t)p.in_h * p.in_w;
+  const int stage_floats = US_RS * p.row_stride;
+
+  if (warp == NCONS / 32) {
+    // ================= producer warp: lane rr prepares and issues the copy of row rr of the stage =================
+    const uintptr_t t_begin = reinterpret_cast<uintptr_t>(p.in);
+    const uintptr_t t_end = t_begin + (uintptr_t)(p.planes * plane_elems) * 4u;
+    uint32_t it = 0;
+    for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const UsItem<UP, DOWN> g(p, item);
+      const int n_st = (g.n_rows + US_RS - 1) / US_RS;
+      const int D = g.colbase + (g.ix_lo - g.ix0);         // multiple of 4 floats: the copies land 16-byte aligned
+      const int64_t e_item = (g.plane * p.in_h + g.iy_first) * (int64_t)p.in_w + g.ix_lo;
+      for (int s = 0; s < n_st; ++s, ++it) {
+        const int slot = (int)(it % (uint32_t)US_STAGES);
+        const uint32_t ph = (it / (uint32_t)US_STAGES) & 1u;
+        mbar_wait(empty_bar(slot), ph ^ 1u, 40);
+        float* const sstage = ring + (size_t)slot * stage_floats;
+        const int r = s * US_RS + lane;
+        const int iy = g.iy_first + r;
+        // 0: nothing (past the item: the consumers discard what they compute from the stale row), 1: bulk copy, 2: zero padding,
+        // 3: copy that would touch bytes outside the tensor (its first / last row): ordinary loads
+        int kind = 0;
+        uint32_t nbytes = 0, lead = 0;
+        int64_t e = 0;
+        if (lane < US_RS && r < g.n_rows) {
+          if (iy < 0 || iy >= p.in_h || g.n_cols <= 0) kind = 2;
+          else {
+            e = e_item + (int64_t)r * p.in_w;
+            const uintptr_t addr = t_begin + (uintptr_t)e * 4u;
+            const uintptr_t addr_al = addr & ~(uintptr_t)15;
+            lead = (uint32_t)(addr - addr_al) >> 2;
+            nbytes = ((lead + (uint32_t)g.n_cols) * 4u + 15u) & ~15u;
+            if (addr_al >= t_begin && addr_al + nbytes <= t_end) {
+              kind = 1;
+              bulk_load_1d(smem_u32(sstage + (size_t)lane * p.row_stride + D), reinterpret_cast<const void*>(addr_al), nbytes, full_bar(slot));
+            } else { kind = 3; nbytes = 0; }
+          }
+        }
+        uint32_t bytes = kind == 1 ? nbytes : 0u;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);   // lanes 0..7 hold the rows
+        unsigned zmask = __ballot_sync(0xffffffffu, kind == 2), emask = __ballot_sync(0xffffffffu, kind == 3);
+        while (zmask) {
+          const int rr = __ffs(zmask) - 1; zmask &= zmask - 1;
+          float* srow = sstage + (size_t)rr * p.row_stride;
+          for (int c = lane; c < p.row_stride; c += 32) srow[c] = 0.f;
+        }
+        while (emask) {
+          const int rr = __ffs(emask) - 1; emask &= emask - 1;
+          const int64_t er = __shfl_sync(0xffffffffu, e, rr);
+          const int ld = (int)__shfl_sync(0xffffffffu, lead, rr);
+          float* srow = sstage + (size_t)rr * p.row_stride + D + ld;
+          for (int c = lane; c < g.n_cols; c += 32) srow[c] = __ldg(p.in + er + c);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), bytes);
+      }
+    }
+    return;
+  }
+
+  // ================= consumers =================
+  const int tid = threadIdx.x;
+  float kf[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = sk[i];
+  // rank-1 test (UP == DOWN == 1 only): kf = ay (x) bx with bx normalised by the smallest non-zero entry of the pivot row, so that
+  // integer-ratio filters ([1,3,3,1]) factor exactly
+  bool sep = false;
+  float ay[4] = {0.f, 0.f, 0.f, 0.f}, bx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (UP == 1 && DOWN == 1) {
+    // (dynamic indexing: read the taps from shared memory here, the register copy is only indexed statically)
+    int piv = 0;
+    for (int i = 1; i < 16; ++i) if (fabsf(sk[i]) > fabsf(sk[piv])) piv = i;
+    const float pv = fabsf(sk[piv]);
+    const int py = piv >> 2;
+    int cs = piv & 3;
+    for (int i = 0; i < 4; ++i) { const float a = fabsf(sk[py * 4 + i]); if (a > 0.f && a < fabsf(sk[py * 4 + cs])) cs = i; }
+    if (pv > 0.f) {
+      const float den = sk[py * 4 + cs];
+      float worst = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { bx[i] = sk[py * 4 + i] / den; ay[i] = sk[i * 4 + cs]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) worst = fmaxf(worst, fabsf(kf[j * 4 + i] - ay[j] * bx[i]));
+      sep = worst <= 2e-7f * pv;
+    }
+  }
+  const unsigned in_addr_lo = (unsigned)((reinterpret_cast<uintptr_t>(p.in) >> 2) & 3u);
+  const bool out16 = (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 && (p.out_w & 3) == 0;
+
+  uint32_t it = 0;
+  for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    const UsItem<UP, DOWN> g(p, item);
+    const int n_st = (g.n_rows + US_RS - 1) / US_RS;
+    // ring column of input column ix0 in row r: colbase + lead(r), lead(r) = ((in >> 2) + e_row) & 3 with
+    // e_row = (plane*in_h + iy_first + r)*in_w + ix_lo; only the low two bits matter, so the running sum may wrap
+    unsigned lead_acc = (unsigned)(((g.plane * p.in_h + g.iy_first) * (int64_t)p.in_w + g.ix_lo) & 3) + in_addr_lo;
+    const unsigned in_w_u = (unsigned)p.in_w;
+    float* const oplane = p.out + g.plane * (int64_t)p.out_h * p.out_w;
+
+    if (UP == 1 && DOWN == 1) {
+      const int ox = g.ox0 + 4 * tid;
+      unsigned mbits = 0;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { const int ix = g.ix0 + 4 * tid + i; mbits |= (ix >= 0 && ix < p.in_w) ? (1u << i) : 0u; }
+      float acc[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+      // input row r completes output row oy_a + r - 3: stored for 3 <= r < n_rows
+      int64_t oidx = (int64_t)(g.oy_a - 3) * p.out_w + ox;
+      const unsigned r_span = (unsigned)(g.n_rows - 3);
+      const bool vec = out16 && ox + 3 < p.out_w;
+      for (int s = 0; s < n_st; ++s, ++it) {
+        const int slot = (int)(it % (uint32_t)US_STAGES);
+        mbar_wait(full_bar(slot), (it / (uint32_t)US_STAGES) & 1u, 41);
+        const float* srow = ring + (size_t)slot * stage_floats + 4 * tid;
+        const int r0 = s * US_RS - 3;
+#define US_BLUR_ROW(SEPV, RRV)                                                                                   \
+        switch (off & 3u) {                                                                                      \
+          case 0: us_blur_row4<SEPV, RRV, 0>(sp4, mbits, kf, ay, bx, acc); break;                                \
+          case 1: us_blur_row4<SEPV, RRV, 1>(sp4, mbits, kf, ay, bx, acc); break;                                \
+          case 2: us_blur_row4<SEPV, RRV, 2>(sp4, mbits, kf, ay, bx, acc); break;                                \
+          default: us_blur_row4<SEPV, RRV, 3>(sp4, mbits, kf, ay, bx, acc); break;                               \
+        }
+#pragma unroll
+        for (int rr = 0; rr < US_RS; ++rr) {
+          const unsigned off = (unsigned)g.colbase + (lead_acc & 3u);              // 0..6: float4 index off >> 2, shift off & 3
+          const float4* sp4 = reinterpret_cast<const float4*>(srow + (off & ~3u));
+          if (sep) {
+            switch (rr & 3) {
+              case 0: US_BLUR_ROW(true, 0) break;
+              case 1: US_BLUR_ROW(true, 1) break;
+              case 2: US_BLUR_ROW(true, 2) break;
+              default: US_BLUR_ROW(true, 3) break;
+            }
+          } else {
+            switch (rr & 3) {
+              case 0: US_BLUR_ROW(false, 0) break;
+              case 1: US_BLUR_ROW(false, 1) break;
+              case 2: US_BLUR_ROW(false, 2) break;
+              default: US_BLUR_ROW(false, 3) break;
+            }
+          }
+          if ((unsigned)(r0 + rr) < r_span) {
+            const int k = (rr - 3) & 3;
+            float* op = oplane + oidx;
+            if (vec) *reinterpret_cast<float4*>(op) = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
+            else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) if (ox + c < p.out_w) op[c] = acc[c][k];
+            }
+          }
+          oidx += p.out_w; srow += p.row_stride; lead_acc += in_w_u;
+        }
+#undef US_BLUR_ROW
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(slot));
+      }
+    } else if (UP == 1 && DOWN == 2) {
+      const int ox = g.ox0 + tid;
+      const bool col_ok = ox < p.out_w;
+      const bool masked = g.ix0 < 0 || g.ix0 + C::COUNT > p.in_w;     // the strip touches the left / right zero padding
+      bool m[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int ix = g.ix0 + 2 * tid + i; m[i] = ix >= 0 && ix < p.in_w; }
+      float cur = 0.f, prev = 0.f;    // output rows q = oy_a + r/2 and q - 1
+      // the odd input row r completes output row oy_a + (r >> 1) - 1: stored for 3 <= r < n_rows
+      int64_t oidx = (int64_t)(g.oy_a - 1) * p.out_w + ox;
+      const unsigned r_span = (unsigned)(g.n_rows - 3);
+      for (int s = 0; s < n_st; ++s, ++it) {
+        const int slot = (int)(it % (uint32_t)US_STAGES);
+        mbar_wait(full_bar(slot), (it / (uint32_t)US_STAGES) & 1u, 42);
+        const float* srow = ring + (size_t)slot * stage_floats + g.colbase + 2 * tid;
+        const int r0 = s * US_RS - 3;
+#pragma unroll
+        for (int rr = 0; rr < US_RS; ++rr) {
+          const float* sp = srow + (lead_acc & 3u);
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[i] = sp[i]; if (masked) v[i] = m[i] ? v[i] : 0.f; }
+          // u = 2*oy_a + r: even rows carry taps ky = 0 (row q: its first tap) and 2 (row q - 1), odd rows ky = 1 and 3
+          const int k0 = (rr & 1), k1 = (rr & 1) + 2;
+          if (!(rr & 1)) cur = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cur = fmaf(kf[k0 * 4 + i], v[i], cur); prev = fmaf(kf[k1 * 4 + i], v[i], prev); }
+          if (rr & 1) {
+            if ((unsigned)(r0 + rr) < r_span && col_ok) oplane[oidx] = prev;
+            oidx += p.out_w;
+            prev = cur;
+          }
+          srow += p.row_stride; lead_acc += in_w_u;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(slot));
+      }
+    } else {
+      // UP == 2: thread t owns input columns ix0 + 4t .. +5 and output columns X = ox0 + 8t + n, n = 0..7
+      const int X = g.ox0 + 8 * tid;
+      const int q0 = (g.ox0 - p.pad_x0) & 1;
+      unsigned mbits = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const int ix = g.ix0 + 4 * tid + i; mbits |= (ix >= 0 && ix < p.in_w) ? (1u << i) : 0u; }
+      float pv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // taps of the two output rows an input row completes (e = 0: ky = 1, 3; e = 1: ky = 0, 2) for both column parities
+      float w[2][2][4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kyf = e ? 0 : 1, kys = kyf + 2;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          w[e][q][0] = kf[kyf * 4 + q]; w[e][q][1] = kf[kyf * 4 + q + 2];
+          w[e][q][2] = kf[kys * 4 + q]; w[e][q][3] = kf[kys * 4 + q + 2];
+        }
+      }
+      // with iy = iy_first + r as the second input row: output rows oy = 2*iy - 3 + pad and oy + 1
+      int oy = 2 * g.iy_first - 3 + p.pad_y0;
+      int64_t oidx = (int64_t)oy * p.out_w + X;
+      const bool vec = out16 && X + 7 < p.out_w;
+      for (int s = 0; s < n_st; ++s, ++it) {
+        const int slot = (int)(it % (uint32_t)US_STAGES);
+        mbar_wait(full_bar(slot), (it / (uint32_t)US_STAGES) & 1u, 43);
+        const float* srow = ring + (size_t)slot * stage_floats + 4 * tid;
+#define US_UP_ROW(Q0V)                                                                \
+        switch (off & 3u) {                                                           \
+          case 0: us_up_row8<Q0V, 0>(sp4, mbits, w, pv, y); break;                    \
+          case 1: us_up_row8<Q0V, 1>(sp4, mbits, w, pv, y); break;                    \
+          case 2: us_up_row8<Q0V, 2>(sp4, mbits, w, pv, y); break;                    \
+          default: us_up_row8<Q0V, 3>(sp4, mbits, w, pv, y); break;                   \
+        }
+#pragma unroll
+        for (int rr = 0; rr < US_RS; ++rr) {
+          const unsigned off = (unsigned)g.colbase + (lead_acc & 3u);
+          const float4* sp4 = reinterpret_cast<const float4*>(srow + (off & ~3u));
+          float y[2][8];
+          if (q0) { US_UP_ROW(1) } else { US_UP_ROW(0) }
+          const bool first = (s == 0 && rr == 0);                    // no previous row yet
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (!first && oy + e >= g.oy_a && oy + e < g.oy_b) {
+              float* op = oplane + oidx + (e ? p.out_w : 0);
+              if (vec) {
+                *reinterpret_cast<float4*>(op) = make_float4(y[e][0], y[e][1], y[e][2], y[e][3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(y[e][4], y[e][5], y[e][6], y[e][7]);
+              } else {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) if (X + n < p.out_w) op[n] = y[e][n];
+              }
+            }
+          }
+          oy += 2; oidx += 2 * (int64_t)p.out_w; srow += p.row_stride; lead_acc += in_w_u;
+        }
+#undef US_UP_ROW
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(slot));
+      }
+    }
+  }
+}
+
+template <int UP, int DOWN>
+int launch_stream(const float* in, const float* kernel, float* out, int64_t planes, int in_h, int in_w, int out_h, int out_w,
+                  int pad_x0, int pad_y0, cudaStream_t st) {
+  using C = UsCfg<UP, DOWN>;
+  UsArgs a;
+  a.in = in; a.kernel = kernel; a.out = out; a.planes = planes;
+  a.in_h = in_h; a.in_w = in_w; a.out_h = out_h; a.out_w = out_w; a.pad_x0 = pad_x0; a.pad_y0 = pad_y0;
+  const int dmax = pad_x0 > 0 ? (((pad_x0 + UP - 1) / UP + 3) & ~3) : 0;
+  // data + left pad + colbase / lead (<= 6) + the vector readers' overshoot (<= 12 floats past the last needed column) + copy tail
+  a.row_stride = (C::COUNT + dmax + 6 + 12 + 4 + 3) & ~3;
+  const size_t smem = (size_t)US_STAGES * US_RS * a.row_stride * sizeof(float);
+  static bool attr_done[3] = {false, false, false};
+  constexpr int which = (UP == 2) ? 2 : (DOWN == 2 ? 1 : 0);
+  if (!attr_done[which]) {
+    VT_CUDA(cudaFuncSetAttribute(upfirdn2d_stream_kernel<UP, DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done[which] = true;
+  }
+  int occ = 0;
+  VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, upfirdn2d_stream_kernel<UP, DOWN>, C::NCONS + 32, smem));
+  VT_CHECK(occ >= 1, "upfirdn2d: the streaming kernel does not fit (%zu B of shared memory)", smem);
+  const int64_t slots = (int64_t)vt_num_sms() * occ;
+  a.strips = (int)vt_cdiv(out_w, C::OWT);
+  // enough items for ~4 rounds over the resident blocks, chunks of at least 32 output rows (3 halo rows are re-read per chunk)
+  int64_t chunks = vt_cdiv(4 * slots, planes * a.strips);
+  const int64_t max_chunks = vt_cdiv(out_h, 32);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  a.rows_per_chunk = (int)vt_cdiv(out_h, chunks);
+  a.chunks = (int)vt_cdiv(out_h, a.rows_per_chunk);
+  a.total_items = planes * a.chunks * a.strips;
+  const int64_t grid = a.total_items < slots ? a.total_items : slots;
+  upfirdn2d_stream_kernel<UP, DOWN><<<(unsigned)grid, C::NCONS + 32, smem, st>>>(a);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int vt_upfirdn2d_out_size(int in_h, int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
@@ -262,8 +721,18 @@ extern "C" int vt_upfirdn2d_f32(const float* in, const float* kernel, float* out
   VT_CHECK(planes >= 0 && in_h >= 1 && in_w >= 1, "upfirdn2d: bad input shape");
   VT_CHECK(out_h >= 1 && out_w >= 1, "upfirdn2d: empty output (%d x %d)", out_h, out_w);
   if (planes == 0) return 0;
-  if (g_upfirdn_tiled && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && planes <= 65535 &&
-      ((up_x == 1 && down_x <= 2) || (up_x == 2 && down_x == 1))) {
+  const bool hot4 = kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && ((up_x == 1 && down_x <= 2) || (up_x == 2 && down_x == 1));
+  if (g_upfirdn_tiled >= 2 && hot4 && pad_x0 >= -(1 << 20) && pad_x0 <= 64 && pad_y0 >= -(1 << 20) && pad_y0 <= (1 << 20) &&
+      (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
+    int rc;
+    if (up_x == 2) rc = launch_stream<2, 1>(in, kernel, out, planes, in_h, in_w, out_h, out_w, pad_x0, pad_y0, (cudaStream_t)stream);
+    else if (down_x == 2) rc = launch_stream<1, 2>(in, kernel, out, planes, in_h, in_w, out_h, out_w, pad_x0, pad_y0, (cudaStream_t)stream);
+    else rc = launch_stream<1, 1>(in, kernel, out, planes, in_h, in_w, out_h, out_w, pad_x0, pad_y0, (cudaStream_t)stream);
+    if (rc) return rc;
+    VT_LAUNCH_CHECK();
+    return 0;
+  }
+  if (g_upfirdn_tiled && hot4 && planes <= 65535) {
     // the hot-path instances: compile-time up/down, 4 x 4 register micro-tiles
     int rc;
     if (up_x == 2) rc = launch_k4<2, 1>(in, kernel, out, planes, in_h, in_w, out_h, out_w, pad_x0, pad_y0, (cudaStream_t)stream);

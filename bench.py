@@ -156,28 +156,43 @@ def _pick_threads(make_small, threads=None):
     return best[0]
 
 
-def cpu_reference(cfg, steps, warmup, threads=None):
+def cpu_reference(cfg, steps, warmup, threads=None, budget_s=None):
     """Time the oracle port of the reference CPU path (model/stylegan/op_cpu + F.conv2d) on the host cores: every timed step is
-    ONE full-size unit of the configuration (a 576x1024 frame for configs[1]; ~25 s on 16 cores), B = 1."""
+    ONE full-size unit of the configuration (a 576x1024 frame for configs[1]; ~25 s on 16 cores), B = 1.
+
+    ``budget_s`` (the reference arm): the warm-up frame is timed; only if ``steps`` full-size frames would not fit the budget on
+    this host (slow or busy cores) the timed steps fall back to the largest frame of the same aspect that does, and the value is
+    scaled by pixels - stated in ``sample``.  On the pool's 16-core hosts 20 full frames take ~8 min and fit."""
     import torch
+    scale_note, px_scale = "", 1.0
     with torch.no_grad():
         full, make = _cpu_setup(cfg)
         threads = _pick_threads(make, threads)
         torch.set_num_threads(threads)
         if make is not None:
             make(72, 128)()                                   # thread pool / oneDNN primitive cache
+        t_w = None
         for _ in range(warmup):
-            full()
+            t0 = time.time(); full(); t_w = time.time() - t0
+        if budget_s is not None and t_w is not None and make is not None and steps * t_w > budget_s:
+            for num, den in ((3, 4), (1, 2), (3, 8), (1, 4)):            # same aspect, multiples of 8 pixels
+                h, w = cfg["H"] * num // den // 8 * 8, cfg["W"] * num // den // 8 * 8
+                px_scale = (h * w) / float(cfg["H"] * cfg["W"])
+                if steps * t_w * px_scale <= budget_s or (num, den) == (1, 4):
+                    break
+            full = make(h, w)
+            scale_note = (f"; {steps} full-size frames would take {steps * t_w:.0f} s on this host (> {budget_s:.0f} s budget): timed on "
+                          f"{h}x{w} frames ({px_scale:.3f} of the pixels) and scaled by pixels")
         t0 = time.time()
         for _ in range(steps):
             full()
-        dt = (time.time() - t0) / max(1, steps)
+        dt = (time.time() - t0) / max(1, steps) / px_scale
     ups = 1.0 / dt
     what = (f"Generator({cfg['size']}) image" if cfg["kind"] == "generator" else f"VToonify-{'D' if cfg['backbone'] == 'dualstylegan' else 'T'} "
             f"{cfg['H']}x{cfg['W']} frame")
     return ups, dt, {"kind": "port", "cores": threads, "value": ups, "unit": cfg["unit"], "cpu_model": cpu_model(),
                      "sample": f"oracle port of the reference op_cpu path, one full-size {what} per step (B=1), {dt:.2f} s/step, "
-                               f"torch CPU fp32 {torch.__version__}, {threads} threads on {cpu_model()}"}
+                               f"torch CPU fp32 {torch.__version__}, {threads} threads on {cpu_model()}{scale_note}"}
 
 
 def workload_config(cfg, args, world):
@@ -199,7 +214,7 @@ def run_reference(args, cfg, rank, world):
         return
     # one small-frame pass is the warm-up of the CPU arm (thread pool, primitive cache): repeating the 25 s frame W times would
     # only burn minutes; the K timed steps are full-size frames
-    ups, dt, cb = cpu_reference(cfg, args.steps, 1 if args.warmup > 0 else 0)
+    ups, dt, cb = cpu_reference(cfg, args.steps, 1 if args.warmup > 0 else 0, budget_s=args.ref_budget)
     conf = workload_config(cfg, args, world)       # the same workload description as the GPU arm's (the CPU runs it one unit at a time)
     line = {"impl": "reference", "metric": cfg["metric"], "value": ups, "unit": cfg["unit"], "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -670,6 +685,8 @@ def main():
     ap.add_argument("--wire", default="u8", choices=["u8", "f32"], help="--config video: what crosses PCIe / NVLink on the input side")
     ap.add_argument("--graph", action="store_true", help="end-to-end legs replay one captured CUDA graph per input geometry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=660.0,
+                    help="--impl reference: seconds the K timed CPU steps may take; full-size frames unless the host is too slow for that")
     ap.add_argument("--no-u8", action="store_true", help="skip the uint8-wire / on-device parsing end-to-end leg")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])

@@ -5,6 +5,6 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out
 for tool in memcheck racecheck; do
-  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_case.py > gpurun_out/sanitizer_${TAG}_$tool.log 2>&1
+  PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_case.py > gpurun_out/sanitizer_${TAG}_$tool.log 2>&1
   echo "$tool rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|sanitize_case: done' gpurun_out/sanitizer_${TAG}_$tool.log | tr '\n' ' ')"
 done

@@ -42,6 +42,24 @@ t = ops.conv_transpose2d_s2_k3_nhwc(x, ops.prep_weights((torch.randn((32, 64, 3,
 ops.fir_nhwc(t, K4, (1, 1), bias=torch.zeros(32, device=dev), act=True)
 xp = torch.randn((2, 3, 20, 24), generator=g).to(dev)
 ops.upfirdn2d_planar(xp, K4, (2, 2), (1, 1), (2, 1, 2, 1)); ops.upfirdn2d_planar(xp, K4, (1, 1), (2, 2), (1, 1, 1, 1))
+# streaming upfirdn2d (bulk-copy ring): rows of 4k+1 floats (every copy lead), several strips / chunks / ring laps, a tensor that
+# starts 4 bytes into its allocation (with PYTORCH_NO_CUDA_MEMORY_CACHING=1 every tensor is its own cudaMalloc: exact bounds)
+for shape in ((2, 3, 70, 1025), (1, 2, 9, 7), (1, 1, 130, 2053)):
+    xs = torch.randn(shape, generator=g).to(dev)
+    ops.upfirdn2d_planar(xs, K4 / 4, (1, 1), (1, 1), (1, 1, 1, 1)); ops.upfirdn2d_planar(xs, K4 / 4, (1, 1), (1, 1), (2, 2, 2, 2))
+    ops.upfirdn2d_planar(xs, K4, (2, 2), (1, 1), (2, 1, 2, 1)); ops.upfirdn2d_planar(xs, K4 / 4, (1, 1), (2, 2), (1, 1, 1, 1))
+    ops.upfirdn2d_planar(xs, torch.randn((4, 4), generator=g).to(dev), (1, 1), (1, 1), (1, 1, 1, 1))
+buf = torch.randn(2 * 37 * 131 + 1, generator=g).to(dev)
+ops.upfirdn2d_planar(buf[1:].view(1, 2, 37, 131), K4 / 4, (1, 1), (1, 1), (1, 1, 1, 1))
+# image-only last layer (row-strip kernel, out = NULL), row-strip up-conv, mask head (input-stationary small-N kernel)
+ops.set_option("rs_conv", True)
+rgb1 = {"w": torch.randn((1, 1, 3, 32), generator=g).to(dev), "bias": torch.zeros(3, device=dev), "skip": None, "kernel": None, "only": True}
+conv(1, 32, 32, 18, 272, rgb=rgb1)
+ops.set_option("rs_conv", False)
+xu = torch.randn((1, 10, 256, 64), generator=g).to(dev)
+ops.conv_up2_rs_nhwc(xu, w_for(32, 64), K4, bias=torch.zeros(32, device=dev), act=1)
+xm = torch.randn((1, 40, 70, 64), generator=g).to(dev); xm2 = torch.randn((1, 40, 70, 64), generator=g).to(dev)
+ops.smalln_conv(xm, w_for(1, 128), ops.conv_taps(3, 1), 1, 1, 40, 70, bias=torch.zeros(1, device=dev), act=_lib.ACT_RELU_TANH, src2=xm2)
 ops.fused_bias_act(xp, torch.zeros(3, device=dev), 0.2, 1.4)
 fr = torch.randint(0, 256, (2, 33, 47, 3), generator=g, dtype=torch.uint8).to(dev)
 ops.frame_prefilter_resize(fr, 2, (20, 15), (1, 14, 2, 19))

@@ -391,7 +391,9 @@ upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
   auto full_bar = [&](int s) { return bar0 + (uint32_t)s * 8u; };
   auto empty_bar = [&](int s) { return bar0 + (uint32_t)(US_STAGES + s) * 8u; };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < US_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NCONS / 32); }
+    // every thread that writes / reads a ring row through the generic proxy arrives itself (no lane-0 proxies: the ordering is then
+    // explicit per thread, and compute-sanitizer's racecheck can follow it)
+    for (int s = 0; s < US_STAGES; ++s) { mbar_init(full_bar(s), 32); mbar_init(empty_bar(s), NCONS); }
     fence_barrier_init();
   }
   if (threadIdx.x < 16) sk[threadIdx.x] = p.kernel[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)];   // flipped: true convolution
@@ -451,8 +453,7 @@ upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
           float* srow = sstage + (size_t)rr * p.row_stride + D + ld;
           for (int c = lane; c < g.n_cols; c += 32) srow[c] = __ldg(p.in + er + c);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), bytes);
+        if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), bytes); else mbar_arrive(full_bar(slot));
       }
     }
     return;
@@ -557,8 +558,7 @@ upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
           oidx += p.out_w; srow += p.row_stride; lead_acc += in_w_u;
         }
 #undef US_BLUR_ROW
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(slot));
+        mbar_arrive(empty_bar(slot));
       }
     } else if (UP == 1 && DOWN == 2) {
       const int ox = g.ox0 + tid;
@@ -594,8 +594,7 @@ upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
           }
           srow += p.row_stride; lead_acc += in_w_u;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(slot));
+        mbar_arrive(empty_bar(slot));
       }
     } else {
       // UP == 2: thread t owns input columns ix0 + 4t .. +5 and output columns X = ox0 + 8t + n, n = 0..7
@@ -654,8 +653,7 @@ upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
           oy += 2; oidx += 2 * (int64_t)p.out_w; srow += p.row_stride; lead_acc += in_w_u;
         }
 #undef US_UP_ROW
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(slot));
+        mbar_arrive(empty_bar(slot));
       }
     }
   }

@@ -247,6 +247,19 @@ def gather_frames(local_outputs: Sequence[torch.Tensor], num_batches: int, examp
     return ordered
 
 
+class _Pending:
+    """An asynchronous collective: ``wait()`` orders the CURRENT stream (CUDA) / the caller (CPU) behind the communication
+    work and behind everything the issuing stream had enqueued when the collective was issued (the local piece)."""
+
+    def __init__(self, work, event, device=None):
+        self.work, self.event, self.device = work, event, device
+
+    def wait(self):
+        self.work.wait()
+        if self.event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.event)
+
+
 class ShardedFrameLoop:
     """The reference's single-decoder frame loop over ``world`` GPUs: rank 0 owns the clip (input batches in, frames out),
     every round ``r`` it scatters batch ``r*world + k`` to rank ``k`` and gathers the ``world`` result batches back.
@@ -284,6 +297,13 @@ class ShardedFrameLoop:
     def _side(self):
         return torch.cuda.stream(self.side) if self.cuda else contextlib.nullcontext()
 
+    def _event_on(self, stream):
+        if not self.cuda:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
     def _issue_scatter(self, r, num_batches, stage):
         """stage + scatter round r on the side stream; returns the Work handle (None past the last round)."""
         if r * self.world >= num_batches:
@@ -300,7 +320,13 @@ class ShardedFrameLoop:
                 self.scatter_bytes += sum(c.numel() * c.element_size() for c in chunk[1:])
             else:
                 work = dist.scatter(recv, None, src=self.src, group=self.group, async_op=True)
-        return work
+            # a rank's OWN piece of a scatter / gather is a plain device copy that the backend may enqueue on the issuing stream
+            # instead of its communication stream: consumers wait for the Work AND for this event
+            ev = None
+            if self.cuda:
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+        return _Pending(work, ev, self.device if self.cuda else None)
 
     def run(self, num_batches: int, stage: Optional[Callable] = None, sink: Optional[Callable] = None) -> int:
         """Process ``num_batches`` global batches; returns the number of batches this rank synthesised."""
@@ -330,6 +356,7 @@ class ShardedFrameLoop:
                     cur.wait_event(ev)                  # round r-2's results have left these gather buffers
                 sink_done[s] = []
                 work = dist.gather(self._send[s], self._gath[s], dst=self.src, group=self.group, async_op=True)
+                work = _Pending(work, self._event_on(cur), self.device if self.cuda else None)
                 self.gather_bytes += (self.world - 1) * self._send[s].numel() * self._send[s].element_size()
                 if sink is not None:
                     for k in range(self.world):
@@ -339,7 +366,8 @@ class ShardedFrameLoop:
                             if tok is not None and self.cuda:
                                 sink_done[s].append(tok)
             else:
-                work = dist.gather(self._send[s], None, dst=self.src, group=self.group, async_op=True)
+                work = _Pending(dist.gather(self._send[s], None, dst=self.src, group=self.group, async_op=True), self._event_on(cur),
+                                self.device if self.cuda else None)
             pend_gather[s] = work
             pend_scatter = nxt
         for w in pend_gather:

@@ -46,4 +46,26 @@ __device__ __forceinline__ float vt_round_tf32(float x) {
 
 __device__ __forceinline__ float vt_lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// Rank-1 test of a (flipped) 4x4 FIR kernel held in shared memory: k = ay (x) bx, with bx normalised by the smallest non-zero entry of
+// the pivot row so that integer-ratio filters (outer([1,3,3,1]), every StyleGAN blur) factor exactly.  Returns false for a full-rank
+// kernel (the caller then applies the 16 taps directly).
+__device__ __forceinline__ bool vt_rank1_4x4(const float* sk, float (&ay)[4], float (&bx)[4]) {
+  int piv = 0;
+  for (int i = 1; i < 16; ++i) if (fabsf(sk[i]) > fabsf(sk[piv])) piv = i;
+  const float pv = fabsf(sk[piv]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { ay[i] = 0.f; bx[i] = 0.f; }
+  if (!(pv > 0.f)) return false;
+  const int py = piv >> 2;
+  int cs = piv & 3;
+  for (int i = 0; i < 4; ++i) { const float a = fabsf(sk[py * 4 + i]); if (a > 0.f && a < fabsf(sk[py * 4 + cs])) cs = i; }
+  const float den = sk[py * 4 + cs];
+  float worst = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { bx[i] = sk[py * 4 + i] / den; ay[i] = sk[i * 4 + cs]; }
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 4; ++i) worst = fmaxf(worst, fabsf(sk[j * 4 + i] - ay[j] * bx[i]));
+  return worst <= 2e-7f * pv;
+}
+
 int vt_num_sms();

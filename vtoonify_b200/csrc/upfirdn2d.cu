@@ -468,26 +468,7 @@ upfirdn2d_stream_kernel(const __grid_constant__ UsArgs p) {
   // integer-ratio filters ([1,3,3,1]) factor exactly
   bool sep = false;
   float ay[4] = {0.f, 0.f, 0.f, 0.f}, bx[4] = {0.f, 0.f, 0.f, 0.f};
-  if (UP == 1 && DOWN == 1) {
-    // (dynamic indexing: read the taps from shared memory here, the register copy is only indexed statically)
-    int piv = 0;
-    for (int i = 1; i < 16; ++i) if (fabsf(sk[i]) > fabsf(sk[piv])) piv = i;
-    const float pv = fabsf(sk[piv]);
-    const int py = piv >> 2;
-    int cs = piv & 3;
-    for (int i = 0; i < 4; ++i) { const float a = fabsf(sk[py * 4 + i]); if (a > 0.f && a < fabsf(sk[py * 4 + cs])) cs = i; }
-    if (pv > 0.f) {
-      const float den = sk[py * 4 + cs];
-      float worst = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { bx[i] = sk[py * 4 + i] / den; ay[i] = sk[i * 4 + cs]; }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) worst = fmaxf(worst, fabsf(kf[j * 4 + i] - ay[j] * bx[i]));
-      sep = worst <= 2e-7f * pv;
-    }
-  }
+  if (UP == 1 && DOWN == 1) sep = vt_rank1_4x4(sk, ay, bx);
   const unsigned in_addr_lo = (unsigned)((reinterpret_cast<uintptr_t>(p.in) >> 2) & 3u);
   const bool out16 = (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 && (p.out_w & 3) == 0;
 

@@ -16,13 +16,16 @@ print(order[len(order)//2])
 PY
 )
 echo "conv_tc median launch index: $MEDIAN"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_rs -c 3 \
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_rs_kernel -c 3 \
     -f -o gpurun_out/ncu_${TAG}_rs python tools/profile_step.py > gpurun_out/ncu_${TAG}_rs.log 2>&1
 ncu -i gpurun_out/ncu_${TAG}_rs.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_rs.raw.csv 2>/dev/null
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_rsu_kernel -c 3 \
+    -f -o gpurun_out/ncu_${TAG}_rsu python tools/profile_step.py > gpurun_out/ncu_${TAG}_rsu.log 2>&1
+ncu -i gpurun_out/ncu_${TAG}_rsu.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_rsu.raw.csv 2>/dev/null
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tc -s $MEDIAN -c 1 \
     -f -o gpurun_out/ncu_${TAG}_median python tools/profile_step.py > gpurun_out/ncu_${TAG}_median.log 2>&1
 ncu -i gpurun_out/ncu_${TAG}_median.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_median.raw.csv 2>/dev/null
-python tools/ncu_summary.py gpurun_out/ncu_${TAG}_rs.raw.csv gpurun_out/ncu_${TAG}_median.raw.csv > gpurun_out/ncu_full_${TAG}.json
+python tools/ncu_summary.py gpurun_out/ncu_${TAG}_rs.raw.csv gpurun_out/ncu_${TAG}_rsu.raw.csv gpurun_out/ncu_${TAG}_median.raw.csv > gpurun_out/ncu_full_${TAG}.json
 python - <<PY
 import json
 d=json.load(open("gpurun_out/ncu_full_${TAG}.json"))

@@ -684,6 +684,7 @@ int g_tc_transpose = 1;   // 1: hand the problem over transposed when that waste
 int g_tc_pair_y = -1;     // -1: automatic pair orientation; 0/1: forced (tests)
 int g_tc_direct_store = 0;  // epilogue output path: 0 = smem staging + TMA store, 1 = direct 128-byte row stores, 2 = direct for N <= 128
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
+int g_tc_s2_halo = 0;  // 1: stride-2 layers may use halo staging (4 parity-view boxes per K chunk, 78 KB for a 3x3) and with it CTA pairs
 int g_tc_strict = 1;  // 1: cluster-scope release arrive in the transform warps (no measurable cost here: 74.43 vs 74.41 frames/s); 0: plain remote arrive
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
@@ -727,6 +728,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mode") == 0) { int old = g_tc_mode; g_tc_mode = value; return old; }
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
+  if (key && strcmp(key, "tc_s2_halo") == 0) { int old = g_tc_s2_halo; g_tc_s2_halo = value; return old; }
   if (key && strcmp(key, "tc_strict") == 0) { int old = g_tc_strict; g_tc_strict = value; return old; }
   if (key && strcmp(key, "tc_direct_store") == 0) { int old = g_tc_direct_store; g_tc_direct_store = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
@@ -886,7 +888,11 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
       tx_bytes += w * h * 128;
       halo_bytes = (int)(vt_cdiv(halo_bytes + w * h * 128, 1024) * 1024);
     }
-    a.halo = can_halo && fits && halo_bytes <= 96 * 1024 && (mt > 1 || tx_bytes <= d->taps * TILE_M * 128 / 2) &&
+    // staged bytes must pay off against one box per tap: at most half of it (stride 2 with tc_s2_halo: 0.6 - a 3x3 / stride-2 layer
+    // stages 4 views x 9 x 17 pixels = 0.53 of the per-tap bytes, and the operand-transform warps touch every staged byte once)
+    const int64_t tap_bytes = (int64_t)d->taps * TILE_M * 128;
+    const bool pays = (d->stride == 2 && g_tc_s2_halo) ? (tx_bytes * 10 <= tap_bytes * 6) : (tx_bytes * 2 <= tap_bytes);
+    a.halo = can_halo && fits && halo_bytes <= 96 * 1024 && (mt > 1 || pays) &&
              2 * halo_bytes + 2 * (bnm / cg) * 128 * tgroup + fixed <= MAX_SMEM;   // at least a 2+2 stage pipeline must fit
     if (!a.halo && mt > 1) continue;
     if (!a.halo) cg = 1;

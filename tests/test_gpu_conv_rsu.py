@@ -13,11 +13,14 @@ def knobs():
     lib = _lib.load()
     old = {k: ops.get_option(k) for k in ("rs_min_width", "rs_fmt", "rsu_conv")}
     ops.set_option("rs_min_width", 1)
+    old_epi = lib.vt_set_option(b"rsu_epi", 1)
+    lib.vt_set_option(b"rsu_epi", old_epi)
     yield lib
     for k, v in old.items():
         ops.set_option(k, v)
     lib.vt_set_option(b"rsu_cg", 0)
     lib.vt_set_option(b"rsu_rows", 0)
+    lib.vt_set_option(b"rsu_epi", old_epi)
 
 
 def _blur():
@@ -52,10 +55,12 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES, ids=[f"rsu{i}" for i in range(len(CASES))])
 @pytest.mark.parametrize("fmt,tol", [("bf16", 5e-5), ("f16", 6e-6)])
-def test_rsu_vs_fp32(knobs, case, fmt, tol):
+@pytest.mark.parametrize("epi", [0, 1], ids=["epi0", "epi1"])   # one output row per pass / both rows per pass (csrc/conv_rsu.cu)
+def test_rsu_vs_fp32(knobs, case, fmt, tol, epi):
     from vtoonify_b200 import ops
     B, Cin, Cout, H, W, wB, cg, rows = case
     lib = knobs
+    lib.vt_set_option(b"rsu_epi", epi)
     lib.vt_set_option(b"rsu_cg", cg)
     lib.vt_set_option(b"rsu_rows", rows)
     ops.set_option("rs_fmt", fmt)
@@ -68,7 +73,7 @@ def test_rsu_vs_fp32(knobs, case, fmt, tol):
     assert tuple(y.shape) == (B, 2 * H, 2 * W, Cout)
     scale = ref.abs().max().item()
     err = (y - ref).abs().max().item()
-    print(f"conv_rsu {case} [{fmt}]: max|err| {err:.3e} (max|ref| {scale:.2f})")
+    print(f"conv_rsu {case} [{fmt}, epi {epi}]: max|err| {err:.3e} (max|ref| {scale:.2f})")
     assert err <= tol * scale, f"{err:.3e} > {tol} * {scale:.2f}"
 
 

@@ -73,7 +73,10 @@ __device__ __forceinline__ int ru_slot(int p) { return (p + 2) % RU_S; }   // p 
 
 #define RU_TWAIT(slot, stmt) do { if (p.dbg) { const long long t__ = clock64(); stmt; tw[slot] += clock64() - t__; } else { stmt; } } while (0)
 
-template <int CG>
+// EPI = 0: one output row at a time (4 accumulator loads per row and pixel phase, each waited for on its own);
+// EPI = 1: both output rows of an input row from ONE pass over the five tx rows per pixel phase (10 loads instead of 16, two in
+//          flight per wait), the two dying rows first, so their slots return to the MMA issuer after 7 loads instead of 15.
+template <int CG, int EPI>
 __global__ void __launch_bounds__(RU_THREADS, 1)
 conv_rsu_kernel(const __grid_constant__ RuArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -324,6 +327,38 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_cta0(row_empty(s)); else mbar_arrive(row_empty(s)); }
     };
+    auto free_rows2 = [&](int pp) {   // rows pp and pp + 1: zero both slots (and the mirror), one store wait, two arrives
+      const int sa = ru_slot(pp), sb = ru_slot(pp + 1);
+      ru_zero32(t_lane + (uint32_t)(sa * RU_SLOT)); ru_zero32(t_lane + (uint32_t)(sa * RU_SLOT + 32));
+      ru_zero32(t_lane + (uint32_t)(sb * RU_SLOT)); ru_zero32(t_lane + (uint32_t)(sb * RU_SLOT + 32));
+      if (sa == 0 || sb == 0) { ru_zero32(t_lane + (uint32_t)(RU_S * RU_SLOT)); ru_zero32(t_lane + (uint32_t)(RU_S * RU_SLOT + 32)); }
+      ru_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) { mbar_arrive_cta0(row_empty(sa)); mbar_arrive_cta0(row_empty(sb)); }
+        else { mbar_arrive(row_empty(sa)); mbar_arrive(row_empty(sb)); }
+      }
+    };
+    // noise / bias / activation on one output row's 32 channels of one pixel, then into its 128-byte row of the staging tile
+    auto finish_row = [&](float* acc, float nzv, uint32_t row, int rr) {
+      const float4* bp = reinterpret_cast<const float4*>(cst);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 bq = bp[c4];
+        acc[4 * c4 + 0] = fmaf(acc[4 * c4 + 0], p.acc_scale, bq.x + nzv); acc[4 * c4 + 1] = fmaf(acc[4 * c4 + 1], p.acc_scale, bq.y + nzv);
+        acc[4 * c4 + 2] = fmaf(acc[4 * c4 + 2], p.acc_scale, bq.z + nzv); acc[4 * c4 + 3] = fmaf(acc[4 * c4 + 3], p.acc_scale, bq.w + nzv);
+      }
+      if (p.act == VT_ACT_LRELU) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = vt_lrelu(acc[c], p.slope) * p.gain;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t dst = row + (uint32_t)((kk ^ (rr & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(acc[4 * kk]), "f"(acc[4 * kk + 1]), "f"(acc[4 * kk + 2]), "f"(acc[4 * kk + 3]) : "memory");
+      }
+    };
     for (int strip = cta_i; strip < p.total_strips; strip += cta_n) {
       int b, i0, x0, R;
       strip_geom(strip, b, i0, x0, R);
@@ -348,6 +383,101 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
         float nz[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) nz[j] = nz_next[j];
+        if (EPI == 1) {
+          // The MMA issuer's next input row needs exactly the slots of tx rows 2i-3 and 2i-2: everything before free_rows2() is on
+          // the critical path of the whole pipeline, everything after it overlaps the next row's MMAs.
+          const int Yb = 2 * i - 2;                      // output rows Yb, Yb + 1 <- tx rows Yb-1 .. Yb+3
+          if (lane == 0) tma_store_wait_read<0>();       // both staging buffers (stores of the previous step) are free
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            // Five tx rows j = 0..4 (row Yb-1+j) with weights (g[j], g[j-1]) for the two output rows; the logical slot 0 is the
+            // sum of physical slot 0 and the mirror slot, so the mirror is a sixth entry with its row's weights.  Two register
+            // buffers: a load is issued into a buffer right after its previous content has been consumed.
+            uint32_t u0[32], u1[32];
+            float a0[32], a1[32];
+            const uint32_t tcol = t_lane + (uint32_t)(half * 32);
+            const uint32_t t_mir = tcol + (uint32_t)(RU_S * RU_SLOT);
+            const int s0 = ru_slot(Yb - 1);              // slots of rows j: (s0 + j) % 6
+            const int jm = (6 - s0) % 6;                 // row whose slot is 0 (5: none of the five)
+            auto taddr = [&](int j) { int sj = s0 + j; if (sj >= RU_S) sj -= RU_S; return tcol + (uint32_t)(sj * RU_SLOT); };
+            tmem_ld_32x32_issue(taddr(0), u0);
+            tmem_ld_32x32_issue(taddr(1), u1);
+            if (jm <= 1) {                               // rows 0 / 1 carry the mirror: third load in flight (a0 / a1 are not live yet)
+              uint32_t m[32];
+              tmem_ld_32x32_issue(t_mir, m);
+              tmem_ld_wait();
+              tmem_ld_pin(u0); tmem_ld_pin(u1); tmem_ld_pin(m);
+              const float ma = jm == 0 ? p.g[0] : p.g[1], mb = jm == 0 ? 0.f : p.g[0];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                a0[c] = fmaf(p.g[0], __uint_as_float(u0[c]), 0.f);
+                a0[c] = fmaf(p.g[1], __uint_as_float(u1[c]), a0[c]);
+                a0[c] = fmaf(ma, __uint_as_float(m[c]), a0[c]);
+                a1[c] = fmaf(p.g[0], __uint_as_float(u1[c]), 0.f);
+                a1[c] = fmaf(mb, __uint_as_float(m[c]), a1[c]);
+              }
+            } else {
+              tmem_ld_wait();
+              tmem_ld_pin(u0); tmem_ld_pin(u1);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                a0[c] = fmaf(p.g[0], __uint_as_float(u0[c]), 0.f);
+                a0[c] = fmaf(p.g[1], __uint_as_float(u1[c]), a0[c]);
+                a1[c] = fmaf(p.g[0], __uint_as_float(u1[c]), 0.f);
+              }
+            }
+            if (half == 1) free_rows2(2 * i - 3);        // rows 2i-3, 2i-2 (and their mirror) have been read for the last time
+            tmem_ld_32x32_issue(taddr(2), u0);
+            tmem_ld_32x32_issue(taddr(3), u1);
+            tmem_ld_wait();
+            tmem_ld_pin(u0); tmem_ld_pin(u1);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              a0[c] = fmaf(p.g[2], __uint_as_float(u0[c]), a0[c]);
+              a1[c] = fmaf(p.g[1], __uint_as_float(u0[c]), a1[c]);
+            }
+            // next into u0: the mirror of row 2 / 3 if one of them is slot 0, else row 4
+            const bool mir23 = (jm == 2 || jm == 3);
+            tmem_ld_32x32_issue(mir23 ? t_mir : taddr(4), u0);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              a0[c] = fmaf(p.g[3], __uint_as_float(u1[c]), a0[c]);
+              a1[c] = fmaf(p.g[2], __uint_as_float(u1[c]), a1[c]);
+            }
+            // next into u1: row 4 (after the mirror of 2 / 3), or row 4's own mirror
+            const bool second = mir23 || jm == 4;
+            if (second) tmem_ld_32x32_issue(mir23 ? taddr(4) : t_mir, u1);
+            tmem_ld_wait();
+            tmem_ld_pin(u0);
+            if (mir23) {
+              const float ma = jm == 2 ? p.g[2] : p.g[3], mb = jm == 2 ? p.g[1] : p.g[2];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                a0[c] = fmaf(ma, __uint_as_float(u0[c]), a0[c]);
+                a1[c] = fmaf(mb, __uint_as_float(u0[c]), a1[c]);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) a1[c] = fmaf(p.g[3], __uint_as_float(u0[c]), a1[c]);
+            }
+            if (second) {                                // row 4 or its mirror: weight g[3] on the second output row
+              tmem_ld_pin(u1);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) a1[c] = fmaf(p.g[3], __uint_as_float(u1[c]), a1[c]);
+            }
+            const int rr = 2 * lane + half;              // output pixel inside this warp's 64-pixel run
+            finish_row(a0, nz[half], sbuf0 + (uint32_t)rr * 128u, rr);
+            finish_row(a1, nz[2 + half], sbuf0 + 8192u + (uint32_t)rr * 128u, rr);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.out_map, sbuf0, p.c_base, 2 * (x0 + q * 32), Yb, b);
+            tma_store_4d(&p.out_map, sbuf0 + 8192u, p.c_base, 2 * (x0 + q * 32), Yb + 1, b);
+            tma_store_commit();
+          }
+        } else {
 #pragma unroll
         for (int yi = 0; yi < 2; ++yi) {
           const int Y = 2 * i - 2 + yi;
@@ -395,6 +525,7 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
             tma_store_commit();
           }
           ++n_store;
+        }
         }
         if (k + 1 < R + 2) prefetch(2 * i);              // next iteration's rows 2(i+1)-2, 2(i+1)-1
       }
@@ -450,12 +581,14 @@ fold_upconv_x_kernel(const float* __restrict__ w9, float g0, float g1, float g2,
 }
 
 int g_rsu_cg = 0, g_rsu_rows = 0;
+int g_rsu_epi = 1;   // epilogue form (see the kernel template): 1 = both output rows per pass, dying rows first
 
 }  // namespace
 
 int vt_rsu_set_option(const char* key, int value, int* old) {
   if (key && strcmp(key, "rsu_cg") == 0) { *old = g_rsu_cg; g_rsu_cg = value; return 1; }
   if (key && strcmp(key, "rsu_rows") == 0) { *old = g_rsu_rows; g_rsu_rows = value; return 1; }
+  if (key && strcmp(key, "rsu_epi") == 0) { *old = g_rsu_epi; g_rsu_epi = value; return 1; }
   return 0;
 }
 
@@ -533,8 +666,10 @@ extern "C" int vt_conv_up2_rs(const float* in, const void* w_split, float* out, 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_rsu_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_MAX_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_rsu_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_MAX_SMEM);
+    attr_err = cudaFuncSetAttribute(conv_rsu_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_MAX_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_rsu_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_MAX_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_rsu_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_MAX_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_rsu_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_MAX_SMEM);
   });
   VT_CHECK(attr_err == cudaSuccess, "conv_up2_rs: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   for (int half = 0; half < Cout / 32; ++half) {
@@ -542,7 +677,8 @@ extern "C" int vt_conv_up2_rs(const float* in, const void* w_split, float* out, 
     if (cg == 1) {
       int grid = vt_num_sms();
       if (grid > a.total_strips) grid = a.total_strips;
-      conv_rsu_kernel<1><<<grid, RU_THREADS, smem_bytes, (cudaStream_t)stream>>>(a);
+      if (g_rsu_epi) conv_rsu_kernel<1, 1><<<grid, RU_THREADS, smem_bytes, (cudaStream_t)stream>>>(a);
+      else conv_rsu_kernel<1, 0><<<grid, RU_THREADS, smem_bytes, (cudaStream_t)stream>>>(a);
     } else {
       int pairs = vt_num_sms() / 2;
       if (pairs > a.total_strips) pairs = a.total_strips;
@@ -556,7 +692,8 @@ extern "C" int vt_conv_up2_rs(const float* in, const void* w_split, float* out, 
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      VT_CUDA(cudaLaunchKernelEx(&cfg, conv_rsu_kernel<2>, a));
+      if (g_rsu_epi) VT_CUDA(cudaLaunchKernelEx(&cfg, conv_rsu_kernel<2, 1>, a));
+      else VT_CUDA(cudaLaunchKernelEx(&cfg, conv_rsu_kernel<2, 0>, a));
     }
     VT_LAUNCH_CHECK();
   }

@@ -30,6 +30,7 @@ int vt_validate_conv_desc(const vt_conv_desc* d, const char* who);
 extern int g_upfirdn_tiled;
 extern int g_smalln_is;
 extern int g_fir4;
+extern int g_instnorm_chunks;
 
 namespace {
 
@@ -685,6 +686,8 @@ int g_tc_pair_y = -1;     // -1: automatic pair orientation; 0/1: forced (tests)
 int g_tc_direct_store = 0;  // epilogue output path: 0 = smem staging + TMA store, 1 = direct 128-byte row stores, 2 = direct for N <= 128
 int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap per box; n>1: KB budget
 int g_tc_s2_halo = 0;  // 1: stride-2 layers may use halo staging (4 parity-view boxes per K chunk, 78 KB for a 3x3) and with it CTA pairs
+int g_tc_stage_policy = 1;  // big halo boxes (dilated 3x3): 0 = shrink the weight ring first (3 + 3 stages at dilation 4), 1 = keep >= 5 weight stages and drop to 2 halo stages
+int g_tc_halo_pct = 60;    // halo staging must stage at most this percentage of the per-tap bytes (stride 1)
 int g_tc_strict = 1;  // 1: cluster-scope release arrive in the transform warps (no measurable cost here: 74.43 vs 74.41 frames/s); 0: plain remote arrive
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
@@ -729,11 +732,14 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_mt") == 0) { int old = g_tc_mt; g_tc_mt = value; return old; }
   if (key && strcmp(key, "tc_tgroup") == 0) { int old = g_tc_tgroup; g_tc_tgroup = value; return old; }
   if (key && strcmp(key, "tc_s2_halo") == 0) { int old = g_tc_s2_halo; g_tc_s2_halo = value; return old; }
+  if (key && strcmp(key, "tc_stage_policy") == 0) { int old = g_tc_stage_policy; g_tc_stage_policy = value; return old; }
+  if (key && strcmp(key, "tc_halo_pct") == 0) { int old = g_tc_halo_pct; g_tc_halo_pct = value; return old; }
   if (key && strcmp(key, "tc_strict") == 0) { int old = g_tc_strict; g_tc_strict = value; return old; }
   if (key && strcmp(key, "tc_direct_store") == 0) { int old = g_tc_direct_store; g_tc_direct_store = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
   if (key && strcmp(key, "tc_transpose") == 0) { int old = g_tc_transpose; g_tc_transpose = value; return old; }
   if (key && strcmp(key, "tc_pair_y") == 0) { int old = g_tc_pair_y; g_tc_pair_y = value; return old; }
+  if (key && strcmp(key, "instnorm_chunks") == 0) { int old = g_instnorm_chunks; g_instnorm_chunks = value; return old; }
   if (key && strcmp(key, "fir4") == 0) { int old = g_fir4; g_fir4 = value; return old; }
   if (key && strcmp(key, "smalln_is") == 0) { int old = g_smalln_is; g_smalln_is = value; return old; }
   if (key && strcmp(key, "upfirdn_tiled") == 0) { int old = g_upfirdn_tiled; g_upfirdn_tiled = value; return old; }
@@ -857,7 +863,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   // layer (small-N layers are bound by MMA issue, a pair halves the instructions per pixel), 2 = only N tile 256.
   const int halo1_bytes = d->stride == 1 ? (TILE_W + (dxmax - dxmin)) * (TILE_H + (dymax - dymin)) * 128 : 0;   // (stride 2: decided by the plan below)
   int cg = (g_tc_cg2 && can_halo && (bn == 256 || g_tc_cg2 == 1) && (gWo > TILE_W * mt || gHo > TILE_H) &&
-            halo1_bytes <= d->taps * TILE_M * 128 / 2 && halo1_bytes <= 96 * 1024) ? 2 : 1;
+            (int64_t)halo1_bytes * 100 <= (int64_t)d->taps * TILE_M * 128 * g_tc_halo_pct && halo1_bytes <= 96 * 1024) ? 2 : 1;
   a.tgroup = tgroup;
   for (int t = 0; t < d->taps && t < 32; ++t) {
     if (t % tgroup == 0) a.grp_first_mask |= 1 << t;
@@ -891,7 +897,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     // staged bytes must pay off against one box per tap: at most half of it (stride 2 with tc_s2_halo: 0.6 - a 3x3 / stride-2 layer
     // stages 4 views x 9 x 17 pixels = 0.53 of the per-tap bytes, and the operand-transform warps touch every staged byte once)
     const int64_t tap_bytes = (int64_t)d->taps * TILE_M * 128;
-    const bool pays = (d->stride == 2 && g_tc_s2_halo) ? (tx_bytes * 10 <= tap_bytes * 6) : (tx_bytes * 2 <= tap_bytes);
+    const bool pays = (d->stride == 2 && g_tc_s2_halo) ? (tx_bytes * 10 <= tap_bytes * 6) : ((int64_t)tx_bytes * 100 <= tap_bytes * g_tc_halo_pct);
     a.halo = can_halo && fits && halo_bytes <= 96 * 1024 && (mt > 1 || pays) &&
              2 * halo_bytes + 2 * (bnm / cg) * 128 * tgroup + fixed <= MAX_SMEM;   // at least a 2+2 stage pipeline must fit
     if (!a.halo && mt > 1) continue;
@@ -904,12 +910,17 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
     a.b_stage_bytes = (bnm / cg) * 128 * tgroup;
     a.a_stages = a.halo ? 3 : 4;
     a.b_stages = tgroup > 1 ? 4 : (cg == 2 ? 8 : 6);
+    // a K chunk's MMAs (taps x 6 instructions) cover one halo stage; a weight stage covers one tap only: with big halo boxes a
+    // deeper weight ring hides more TMA latency than a third halo stage (policy 1)
+    const int b_floor = (g_tc_stage_policy == 1 && a.halo && a.a_stage_bytes >= 40 * 1024 && tgroup == 1) ? 5 : 3;
     while (a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed > MAX_SMEM) {
-      if (a.b_stages > 3) --a.b_stages;
+      if (a.b_stages > b_floor) --a.b_stages;
       else if (a.a_stages > 2) --a.a_stages;
       else if (a.b_stages > 2) --a.b_stages;
       else break;
     }
+    if (b_floor > 3)
+      while (a.b_stages < 8 && a.a_stages * a.a_stage_bytes + (a.b_stages + 1) * a.b_stage_bytes + fixed <= MAX_SMEM) ++a.b_stages;
     smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_stage_bytes + fixed;
     if (smem_bytes <= MAX_SMEM || mt == 1) break;
   }

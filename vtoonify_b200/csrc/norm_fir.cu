@@ -319,11 +319,21 @@ fir4_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
 
 }  // namespace
 
+int g_instnorm_chunks = 296;   // target number of chunks per sample on large maps (0: always the small chunks)
+
 static void instnorm_plan(int64_t HW, int C, int64_t* chunk, int64_t* chunks) {
   const int nvec = C / 4;
   const int plan = 256 / nvec;                      // pixels processed concurrently by a block
   int64_t ch = (int64_t)plan * 32;                  // 32 pixels per thread: several blocks per SM even on the 72x128 maps
   if (ch < 64) ch = 64;
+  // Large maps: ~2 chunks per SM and sample instead of thousands of 8-trip blocks (block turnover, not bandwidth, bounded those;
+  // the finalize pass shrinks with the chunk count).  The plan depends on (HW, C) only, never on the batch size: a frame's
+  // statistics must not depend on the batch it travels in.
+  if (g_instnorm_chunks > 0) {
+    const int64_t unit = (int64_t)plan * 4;         // one trip of the main loop
+    const int64_t want = vt_cdiv(vt_cdiv(HW, g_instnorm_chunks), unit) * unit;
+    if (want > ch) ch = want;
+  }
   *chunk = ch;
   *chunks = vt_cdiv(HW, ch);
 }

@@ -610,3 +610,63 @@ def test_adain_affine_table_vs_adain_apply():
     aff = ops.adain_affine(st, gb.cuda())
     y = xn * aff[:, None, None, :, 0] + aff[:, None, None, :, 1]
     assert (y - ref).abs().max().item() <= 1e-5
+
+
+# ---- round-2b scheduling options: same results whichever way they are set ---------------------------------------------
+@pytest.mark.parametrize("opt,values", [(b"tc_warp_store", (0, 1)), (b"tc_stage_policy", (0, 1)), (b"tc_halo_pct", (50, 60, 100))])
+@pytest.mark.parametrize("case", [(2, 512, 512, 24, 40, 3, 1, 4, 4),     # dilation 4: the big-halo stage plan
+                                  (1, 256, 256, 33, 20, 3, 1, 2, 2),
+                                  (2, 64, 128, 19, 45, 3, 1, 1, 1),      # partial tiles in both directions
+                                  (1, 128, 32, 16, 24, 1, 1, 0, 1)])     # 1x1, small N
+def test_tc_scheduling_options_do_not_change_results(case, opt, values):
+    """Per-warp vs CTA-wide output stores, the pipeline-stage plan of big halo boxes and the halo-staging threshold only change
+    WHEN data moves, never what is summed in which order: bit-identical outputs (csrc/conv_tc.cu)."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007 + 5)
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    lib = _lib.load()
+    ops.set_precision("fp32")
+    ref = _run(ops, x, w, b, k, stride, pad, dil, "fp32")
+    outs = []
+    old = lib.vt_set_option(opt, values[0])
+    try:
+        for v in values:
+            lib.vt_set_option(opt, v)
+            outs.append(_run(ops, x, w, b, k, stride, pad, dil, "bf16x3"))
+    finally:
+        lib.vt_set_option(opt, old)
+        ops.set_precision(ops.DEFAULT_PRECISION)
+    assert maxerr(outs[0], ref) <= BF16X3_TOL * max(1.0, ref.abs().max().item())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0]), f"{opt.decode()} changed the result"
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 150, 201), (1, 512, 37, 64), (2, 32, 300, 310)])
+def test_instnorm_chunk_plans_agree(shape):
+    """Small chunks vs ~296 chunks per sample: the same statistics (different partial-sum grouping, double-precision finalize);
+    a sample's statistics do not depend on the batch it is in under either plan (csrc/norm_fir.cu)."""
+    from vtoonify_b200 import _lib, ops
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = ops.to_nhwc((torch.randn((B, C, H, W), generator=g) * 2.0 + 0.5).cuda())
+    x2 = ops.to_nhwc(torch.randn((B, C, H, W), generator=g).cuda())
+    lib = _lib.load()
+    res = {}
+    old = lib.vt_set_option(b"instnorm_chunks", 0)
+    try:
+        for plan in (0, 296, 7):
+            lib.vt_set_option(b"instnorm_chunks", plan)
+            res[plan] = (ops.instnorm_stats(x), ops.instnorm_stats(x, x2))
+            one = ops.instnorm_stats(x[:1].contiguous(), x2[:1].contiguous())
+            assert torch.equal(one, res[plan][1][:1]), "statistics of a sample depend on its batch"
+    finally:
+        lib.vt_set_option(b"instnorm_chunks", old)
+    xc = ops.to_nchw(x).double()
+    mean = xc.mean(dim=(2, 3)); rstd = 1.0 / torch.sqrt(xc.var(dim=(2, 3), unbiased=False) + 1e-5)
+    for plan, (s0, s1) in res.items():
+        assert (s0[:, :, 0].double() - mean).abs().max().item() <= 1e-5, plan
+        assert ((s0[:, :, 1].double() - rstd) / rstd).abs().max().item() <= 1e-5, plan
+        assert (s1 - res[0][1]).abs().max().item() <= 2e-6 * max(1.0, res[0][1].abs().max().item()), plan

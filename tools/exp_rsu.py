@@ -43,15 +43,15 @@ def rsu_case(B, Cin, Cout, H, W):
     fn = lambda: ops.conv_up2_rs_nhwc(x, w9, K4, bias=bias, noise=noise, noise_w=nw, act=1)
     ms = timed(fn)
     print(f"  up {Cin}->{Cout} {H}x{W} B{B}: {ms:7.3f} ms | {roles(fn)}", flush=True)
-    return fn()
 
 
 with torch.no_grad():
-    outs = {}
-    for epi in (0, 1):
-        lib.vt_set_option(b"rsu_epi", epi)
-        print("rsu_epi", epi)
-        outs[epi] = (rsu_case(4, 64, 32, 1152, 2048), rsu_case(4, 128, 64, 576, 1024))
-        rsu_case(8, 64, 32, 512, 512)
-    for a, b in zip(outs[0], outs[1]):
-        print("  epi0 vs epi1 max|diff|", (a - b).abs().max().item(), "max|ref|", a.abs().max().item())
+    for rnd in range(2):
+        for epi, bst in ((0, 4), (1, 4), (1, 6), (0, 6)):
+            lib.vt_set_option(b"rsu_epi", epi)
+            lib.vt_set_option(b"rsu_bstages", bst)
+            print(f"round {rnd}: rsu_epi {epi} rsu_bstages {bst}")
+            rsu_case(4, 64, 32, 1152, 2048)
+            rsu_case(4, 128, 64, 576, 1024)
+    lib.vt_set_option(b"rsu_epi", 1)
+    lib.vt_set_option(b"rsu_bstages", 6)

@@ -130,7 +130,7 @@ def load():
     if lib.vt_abi_version() != ABI_VERSION:
         raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects {ABI_VERSION}")
     for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup"), ("VT_TC_CG2", b"tc_cg2"),
-                     ("VT_TC_DIRECT_STORE", b"tc_direct_store"), ("VT_TC_STRICT", b"tc_strict"), ("VT_TC_STAGE_POLICY", b"tc_stage_policy"), ("VT_TC_HALO_PCT", b"tc_halo_pct"), ("VT_RS_STRICT", b"rs_strict"), ("VT_RSU_EPI", b"rsu_epi"),
+                     ("VT_TC_DIRECT_STORE", b"tc_direct_store"), ("VT_TC_STRICT", b"tc_strict"), ("VT_TC_STAGE_POLICY", b"tc_stage_policy"), ("VT_TC_HALO_PCT", b"tc_halo_pct"), ("VT_RS_STRICT", b"rs_strict"), ("VT_RSU_EPI", b"rsu_epi"), ("VT_TC_WARP_STORE", b"tc_warp_store"),
                      ("VT_INSTNORM_CHUNKS", b"instnorm_chunks")):
         if os.environ.get(env) is not None and os.environ.get(env) != "":
             lib.vt_set_option(key, int(os.environ[env]))      # tuning experiments only

@@ -41,7 +41,7 @@ constexpr int RU_MAX_SMEM = 227 * 1024;
 constexpr int RU_N = 192;                      // 3 tx rows x 2 pixel phases x 32 output channels
 constexpr int RU_SLOT = 64;                    // TMEM columns per tx row
 constexpr int RU_S = 6;                        // logical slots (physical 7: slot 6 mirrors slot 0)
-constexpr int RU_B_STAGES = 4;
+constexpr int RU_B_STAGES_MAX = 8;             // weight-tile ring: 6 stages by default (see vt_conv_up2_rs), 4 in the first version
 constexpr int RU_STAGING = 4 * 2 * 8192;       // per epilogue warp: two 64 px x 128 B buffers
 
 struct RuArgs {
@@ -51,7 +51,7 @@ struct RuArgs {
   int B, H, W, KC, wB;
   int half, c_base;        // output-channel slice of this pass: tile base = half*KC*3, channels [c_base, c_base + 32)
   int rows_per_strip, strips_x, strips_y, total_strips;
-  int a_stages;
+  int a_stages, b_stages;
   int b_tile_bytes;        // (192 / CG) rows x 128 B
   const float* bias; const float* noise; const float* noise_w;
   int act; float slope, gain;
@@ -83,15 +83,15 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)p.a_stages * RU_A_STAGE;
-  const uint32_t st_base = (b_base + (uint32_t)RU_B_STAGES * (uint32_t)p.b_tile_bytes + 1023u) & ~1023u;
+  const uint32_t st_base = (b_base + (uint32_t)p.b_stages * (uint32_t)p.b_tile_bytes + 1023u) & ~1023u;
   const uint32_t cst_base = st_base + RU_STAGING;
   const uint32_t bar_base = cst_base + 32 * 4;
-  // barriers: a_full[8] a_ready[8] a_empty[8] b_full[4] b_empty[4] row_full[8] row_empty[8] | tmem slot
+  // barriers: a_full[8] a_ready[8] a_empty[8] b_full[8] row_full[8] row_empty[8] | tmem slot | b_empty[8]
   auto a_full = [&](int i) { return bar_base + 8u * i; };
   auto a_ready = [&](int i) { return bar_base + 64u + 8u * i; };
   auto a_empty = [&](int i) { return bar_base + 128u + 8u * i; };
   auto b_full = [&](int i) { return bar_base + 192u + 8u * i; };
-  auto b_empty = [&](int i) { return bar_base + 224u + 8u * i; };
+  auto b_empty = [&](int i) { return bar_base + 392u + 8u * i; };
   auto row_full = [&](int i) { return bar_base + 256u + 8u * i; };
   auto row_empty = [&](int i) { return bar_base + 320u + 8u * i; };
   const uint32_t tmem_slot = bar_base + 384u;
@@ -110,7 +110,7 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_ready(i), RU_XFORM_WARPS * CG); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < RU_B_STAGES; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(row_full(i), 1); mbar_init(row_empty(i), 4 * CG); }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -179,7 +179,7 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
               }
             }
             __syncwarp();
-            if (++b_st == RU_B_STAGES) { b_st = 0; b_par ^= 1; }
+            if (++b_st == p.b_stages) { b_st = 0; b_par ^= 1; }
           }
         }
       }
@@ -234,7 +234,7 @@ conv_rsu_kernel(const __grid_constant__ RuArgs p) {
               }
             }
             __syncwarp();
-            if (++b_st == RU_B_STAGES) { b_st = 0; b_par ^= 1; }
+            if (++b_st == p.b_stages) { b_st = 0; b_par ^= 1; }
           }
           if (++a_st == p.a_stages) { a_st = 0; a_par ^= 1; }
         }
@@ -581,6 +581,8 @@ fold_upconv_x_kernel(const float* __restrict__ w9, float g0, float g1, float g2,
 }
 
 int g_rsu_cg = 0, g_rsu_rows = 0;
+int g_rsu_bstages = 6;   // weight-tile ring depth: the MMA issuer consumes a tile per ~1 k cycles, 4 stages left it waiting for weights
+                         // 5-11 % of the time (role timing); 6 stages = all tiles of a row at Cin = 64
 int g_rsu_epi = 1;   // epilogue form (see the kernel template): 1 = both output rows per pass, dying rows first
 
 }  // namespace
@@ -588,6 +590,7 @@ int g_rsu_epi = 1;   // epilogue form (see the kernel template): 1 = both output
 int vt_rsu_set_option(const char* key, int value, int* old) {
   if (key && strcmp(key, "rsu_cg") == 0) { *old = g_rsu_cg; g_rsu_cg = value; return 1; }
   if (key && strcmp(key, "rsu_rows") == 0) { *old = g_rsu_rows; g_rsu_rows = value; return 1; }
+  if (key && strcmp(key, "rsu_bstages") == 0) { *old = g_rsu_bstages; g_rsu_bstages = value; return 1; }
   if (key && strcmp(key, "rsu_epi") == 0) { *old = g_rsu_epi; g_rsu_epi = value; return 1; }
   return 0;
 }
@@ -638,7 +641,12 @@ extern "C" int vt_conv_up2_rs(const float* in, const void* w_split, float* out, 
   const int64_t total = (int64_t)B * a.strips_x * a.strips_y;
   VT_CHECK(total < (1LL << 30), "conv_up2_rs: too many strips");
   a.total_strips = (int)total;
-  const int fixed = RU_B_STAGES * a.b_tile_bytes + 1024 + RU_STAGING + 128 + 512 + 1024;
+  a.b_stages = g_rsu_bstages;
+  VT_CHECK(a.b_stages >= 2 && a.b_stages <= RU_B_STAGES_MAX, "conv_up2_rs: rsu_bstages must be in [2, 8]");
+  const int fixed0 = 1024 + RU_STAGING + 128 + 512 + 1024;
+  // keep at least three activation stages (single-CTA launches hold whole 24 KB weight tiles: 4 of them)
+  while (a.b_stages > 2 && (RU_MAX_SMEM - fixed0 - a.b_stages * a.b_tile_bytes) / RU_A_STAGE < 3) --a.b_stages;
+  const int fixed = a.b_stages * a.b_tile_bytes + fixed0;
   a.a_stages = (RU_MAX_SMEM - fixed) / RU_A_STAGE;
   if (a.a_stages > 6) a.a_stages = 6;
   VT_CHECK(a.a_stages >= 2, "conv_up2_rs: shared memory plan does not fit");

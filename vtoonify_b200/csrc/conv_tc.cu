@@ -80,6 +80,7 @@ struct TcArgs {
   int in_w, in_h;            // kernel-space input extents
   int mma_n;                 // N of one MMA / TMEM columns per accumulator: block_n, or 2*block_n in the N-stacked bf16x3 form
   int nstack;                // bf16x3, Cout == 32: weight rows [w_hi|w_hi] x32 then [w_lo|w_lo] x32 -> 4 MMAs per tap, halves summed in the epilogue
+  int warp_store;            // epilogue: every warp stages and TMA-stores its own 32 pixels (8 x 4 box), no CTA-wide barrier
   int direct_store;          // epilogue writes its 128-byte pixel rows straight to global memory instead of smem staging + TMA store
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
   int bf16x3;                // operands split into bf16 hi/lo in shared memory, 3 MMA products (fp32-class accuracy)
@@ -553,8 +554,16 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
             }
           } else {
           const uint32_t sbuf = st_base + (chunk & 1) * STAGING_BYTES;
-          if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
-          named_bar_sync(1, 128);
+          if (p.warp_store) {
+            // per-warp form: the warp's 32 pixels are rows 4q .. 4q+3 of the tile = a 4 KB slice of the staging buffer (a whole
+            // number of 1 KB swizzle atoms), stored through the same map with a box of 4 rows.  No CTA-wide barrier: a warp that
+            // is ahead starts its next chunk instead of waiting for the slowest one twice per chunk.
+            if (lane == 0) tma_store_wait_read<1>();    // this warp's store of two chunks ago has read the slice
+            __syncwarp();
+          } else {
+            if (store_thread) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
+            named_bar_sync(1, 128);
+          }
           const uint32_t row = sbuf + (uint32_t)r * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -564,10 +573,18 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
                          : "memory");
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (store_thread) {
-            tma_store_4d(&p.out_map[ph], sbuf, nb, ox0 + g * TILE_W, oy0, b);
-            tma_store_commit();
+          if (p.warp_store) {
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.out_map[ph], sbuf + (uint32_t)q * 4096u, nb, ox0 + g * TILE_W, oy0 + q * 4, b);
+              tma_store_commit();
+            }
+          } else {
+            named_bar_sync(1, 128);
+            if (store_thread) {
+              tma_store_4d(&p.out_map[ph], sbuf, nb, ox0 + g * TILE_W, oy0, b);
+              tma_store_commit();
+            }
           }
           }
           if (p.dbg) tw[3] += clock64() - t_st0;
@@ -614,7 +631,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
       }
       if (++as == p.acc_stages) { as = 0; t_par ^= 1; }
     }
-    if (store_thread) tma_store_wait_all<0>();
+    if (p.warp_store ? (lane == 0) : store_thread) tma_store_wait_all<0>();
   }
 
   if (p.dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
@@ -688,6 +705,7 @@ int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap
 int g_tc_s2_halo = 0;  // 1: stride-2 layers may use halo staging (4 parity-view boxes per K chunk, 78 KB for a 3x3) and with it CTA pairs
 int g_tc_stage_policy = 1;  // big halo boxes (dilated 3x3): 0 = shrink the weight ring first (3 + 3 stages at dilation 4), 1 = keep >= 5 weight stages and drop to 2 halo stages
 int g_tc_halo_pct = 60;    // halo staging must stage at most this percentage of the per-tap bytes (stride 1)
+int g_tc_warp_store = 1;   // epilogue: per-warp staging + TMA stores (8 x 4 pixel boxes) instead of one CTA-wide store per chunk
 int g_tc_strict = 1;  // 1: cluster-scope release arrive in the transform warps (no measurable cost here: 74.43 vs 74.41 frames/s); 0: plain remote arrive
 
 int check_supported(const vt_conv_desc* d, bool set_err) {
@@ -734,6 +752,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_s2_halo") == 0) { int old = g_tc_s2_halo; g_tc_s2_halo = value; return old; }
   if (key && strcmp(key, "tc_stage_policy") == 0) { int old = g_tc_stage_policy; g_tc_stage_policy = value; return old; }
   if (key && strcmp(key, "tc_halo_pct") == 0) { int old = g_tc_halo_pct; g_tc_halo_pct = value; return old; }
+  if (key && strcmp(key, "tc_warp_store") == 0) { int old = g_tc_warp_store; g_tc_warp_store = value; return old; }
   if (key && strcmp(key, "tc_strict") == 0) { int old = g_tc_strict; g_tc_strict = value; return old; }
   if (key && strcmp(key, "tc_direct_store") == 0) { int old = g_tc_direct_store; g_tc_direct_store = value; return old; }
   if (key && strcmp(key, "tc_cg2") == 0) { int old = g_tc_cg2; g_tc_cg2 = value; return old; }
@@ -788,6 +807,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   }
   a.dbg = g_tc_dbg;
   a.out = d->out;
+  a.warp_store = g_tc_warp_store ? 1 : 0;
   a.direct_store = (g_tc_direct_store == 1) || (g_tc_direct_store == 2 && d->n_phase * d->Cout <= 128);
   a.slope_vec = d->slope_vec;
   a.rgb_w = d->rgb_w; a.rgb_bias = d->rgb_bias; a.rgb_skip = d->rgb_skip; a.rgb_skip_kernel = d->rgb_skip_kernel; a.rgb_out = d->rgb_out;
@@ -999,7 +1019,7 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   for (int ph = 0; ph < d->n_phase; ++ph) {
     const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)gWo, (uint64_t)gHo, (uint64_t)d->B};
     const uint64_t str[3] = {(uint64_t)g_out_sx * 4, (uint64_t)g_out_sy * 4, (uint64_t)d->out_sb * 4};
-    const uint32_t box[4] = {32, TILE_W, TILE_H, 1};
+    const uint32_t box[4] = {32, TILE_W, (uint32_t)(a.warp_store ? TILE_H / 4 : TILE_H), 1};
     if (make_map4(&a.out_map[ph], d->out + d->phase_off[ph], dims, str, box, "output")) return 1;
   }
   for (int ph = d->n_phase; ph < 4; ++ph) a.out_map[ph] = a.out_map[0];

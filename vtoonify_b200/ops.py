@@ -52,6 +52,8 @@ _options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smal
             "rsu_conv": True, "rsu_max_cin": 128}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
+if _os.environ.get("VT_RSU_MAX_CIN"):
+    _options["rsu_max_cin"] = int(_os.environ["VT_RSU_MAX_CIN"])      # tuning experiments only
 
 
 def use_folded_upconv(cin: int) -> bool:

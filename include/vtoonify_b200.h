@@ -34,9 +34,11 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 4   /* 2: vt_conv_desc gained weight_bf16x3 / bf16x3_nstack / src_scale, vt_smalln_desc src_mask / tsum, vt_split_weights_bf16x3
+#define VT_ABI_VERSION 5   /* 2: vt_conv_desc gained weight_bf16x3 / bf16x3_nstack / src_scale, vt_smalln_desc src_mask / tsum, vt_split_weights_bf16x3
                             * 3: face-parsing helpers (vt_frame_s2d_f32 .. vt_logits_readout_f32 with out_bstride), backward ops, frame pre-filter
-                            * 4: row-strip kernels, vt_conv_desc gained split_fmt / acc_scale */
+                            * 4: row-strip kernels, vt_conv_desc gained split_fmt / acc_scale
+                            * 5: vt_conv_desc gained stats_ws / stats_ws_floats (statistics of the conv output), vt_conv2d_tc_stats_chunks,
+                            *    vt_instnorm_finalize_f32 */
 
 /* ---- library info / errors ------------------------------------------------------------- */
 int         vt_abi_version(void);
@@ -178,6 +180,11 @@ typedef struct vt_conv_desc {
                                  * 1 = fp16 hi + lo (vt_split_weights_f16x3: 11 + 11 mantissa bits, |activation| < 1.3e5)           */
   float   acc_scale;            /* accumulators are multiplied by this before the epilogue (0 = 1): the inverse of the power-of-two
                                  * `scale` given to vt_split_weights_f16x3                                                           */
+  float*  stats_ws;             /* optional (tensor-core kernel, n_phase == 1, no fused ToRGB): instance-norm partial sums of the tensor
+                                 * this launch WRITES, [chunks][B][Cout][2] = (sum, sum of squares) with chunks =
+                                 * vt_conv2d_tc_stats_chunks(desc); vt_instnorm_finalize_f32 turns them into (mean, rstd).  Replaces the
+                                 * separate statistics pass of AdaptiveInstanceNorm (model/dualstylegan.py:10-21) over a conv output   */
+  int64_t stats_ws_floats;      /* capacity of stats_ws in floats                                                                    */
 } vt_conv_desc;
 
 /* fp32-exact CUDA-core implicit GEMM (FFMA). Any shape. */
@@ -186,6 +193,9 @@ int vt_conv2d_direct_f32(const vt_conv_desc* d, void* stream);
  * Cout % 16 == 0, 16B-aligned views. */
 int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream);
 int vt_conv2d_tc_supported(const vt_conv_desc* d);   /* 1 if vt_conv2d_tc_tf32 accepts the descriptor */
+/* number of partial-sum chunks per (sample, channel) that vt_conv2d_tc_tf32 writes to desc->stats_ws for this descriptor under the current
+ * options (-1 + vt_last_error() if the descriptor cannot produce statistics) */
+int vt_conv2d_tc_stats_chunks(const vt_conv_desc* d);
 /* Row-strip tensor-core kernel for the full-resolution 3x3 / stride 1 / padding 1 layers with Cin, Cout in {32, 64} (StyledConv conv2 of
  * the last generator levels, model/stylegan/model.py:298-304 + 364-392): the three vertical taps are stacked along the GEMM N dimension
  * and the partial sums of an output row are accumulated across input rows inside TMEM.  Same descriptor; `weight_bf16x3` must hold the
@@ -206,7 +216,11 @@ int vt_fold_upconv_x_weights_f32(const float* w9, const float* g_host4, float* o
 int vt_conv_up2_rs(const float* in, const void* w_split, float* out, int B, int H, int W, int Cin, int Cout, int wB,
                    const float* g_host4, const float* bias, const float* noise, const float* noise_w, int act,
                    float slope, float gain, int fmt, float acc_scale, void* stream);
-/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","tc_direct_store","smalln_is","fir4","upfirdn_tiled","rs_cg","rs_rows","rs_strict","tc_strict","rsu_cg","rsu_rows"};
+/* tuning knobs for experiments / tests: key in {"tc_mode","tc_mt","tc_tgroup","tc_cg2","tc_transpose","tc_pair_y","tc_direct_store","smalln_is","fir4","upfirdn_tiled","rs_cg","rs_rows","rs_strict","tc_strict","rsu_cg","rsu_rows",
+ * "tc_s2_halo","tc_stage_policy" (1: big halo boxes keep >= 5 weight stages), "tc_halo_pct" (halo staging threshold, % of the per-tap bytes),
+ * "tc_warp_store" (1: per-warp output stores), "rsu_epi" (1: both output rows per epilogue pass), "rsu_bstages" (weight ring depth, 2..8),
+ * "instnorm_chunks" (target chunks per sample on large maps, 0: small chunks)}; none of them changes results beyond fp32 rounding of the
+ * instance-norm partial sums (tests/test_gpu_conv.py, tests/test_gpu_conv_rsu.py);
  * returns the previous value (-1 for an unknown key) */
 int vt_set_option(const char* key, int value);
 /* tuning only: device buffer of 148*16 uint64 that conv_tc fills with per-role wait-cycle counters (NULL disables) */
@@ -262,6 +276,9 @@ int vt_fir_nhwc_f32(const float* in, const float* kernel, float* out, int B, int
 int64_t vt_instnorm_ws_bytes(int B, int64_t HW, int C, int mode);
 int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mode, int B, int64_t HW, int C, int c_stride,
                            float eps, float* stats, void* ws, void* stream);
+/* second stage alone: partial sums ws [chunks][B*Cs][2] = (sum, sum of squares) over HW pixels per entry -> stats [B, Cs, 2] = (mean, rstd);
+ * chunks are added in index order in double precision.  Used with vt_conv_desc.stats_ws (partial sums written by the producing conv). */
+int vt_instnorm_finalize_f32(const float* ws, float* stats, int B, int Cs, int chunks, int64_t HW, float eps, void* stream);
 /* AdaIN as a per-(sample, channel) affine: affine[b][c] = (gamma*rstd, beta - gamma*mean*rstd); stats [B][Cs][2], gamma_beta [B][2*Cs] */
 int vt_adain_affine_f32(const float* stats, const float* gamma_beta, float* affine, int B, int Cs, void* stream);
 /* out[b,p,c] = gamma[b,c] * (x - mean) * rstd + beta[b,c]; gamma_beta: [B, 2*Cs] (gamma then beta) */

@@ -36,8 +36,8 @@ def test_library_exports_every_declared_symbol():
 def test_load_binds_and_reports_version():
     from vtoonify_b200 import _lib
     lib = _lib.load()
-    assert lib.vt_abi_version() == _lib.ABI_VERSION == 4
-    assert b"abi=4" in lib.vt_build_info()
+    assert lib.vt_abi_version() == _lib.ABI_VERSION == 5
+    assert b"abi=5" in lib.vt_build_info()
     assert b"sm_100a" in lib.vt_build_info()
     assert ctypes.sizeof(_lib.ConvDesc) % 8 == 0
 

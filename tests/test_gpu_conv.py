@@ -670,3 +670,46 @@ def test_instnorm_chunk_plans_agree(shape):
         assert (s0[:, :, 0].double() - mean).abs().max().item() <= 1e-5, plan
         assert ((s0[:, :, 1].double() - rstd) / rstd).abs().max().item() <= 1e-5, plan
         assert (s1 - res[0][1]).abs().max().item() <= 2e-6 * max(1.0, res[0][1].abs().max().item()), plan
+
+
+@pytest.mark.parametrize("case", [(4, 512, 512, 72, 128, 3, 1, 1, 1),    # the res-block layer (transposed view, CTA pairs, 2 N tiles)
+                                  (2, 512, 512, 24, 40, 3, 1, 4, 4),     # dilation 4
+                                  (2, 64, 128, 19, 45, 3, 1, 1, 1),      # 2 M tiles per work item, partial tiles
+                                  (1, 128, 32, 16, 24, 1, 1, 0, 1),      # 1x1, N = 32 (4 M tiles per work item)
+                                  (3, 32, 64, 9, 7, 3, 1, 1, 1)])        # smaller than one tile
+@pytest.mark.parametrize("m_major", [0, 1])
+def test_tc_fused_output_statistics(case, m_major):
+    """conv2d_nhwc(want_stats=True): per-tile partial sums written by the epilogue warps + finalize == the separate statistics
+    pass over the stored output (AdaptiveInstanceNorm, model/dualstylegan.py:10-21); a sample's statistics do not depend on its
+    batch; the output itself is untouched."""
+    from vtoonify_b200 import _lib, ops
+    B, Cin, Cout, H, W, k, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 10007 + 9)
+    x = ops.to_nhwc((torch.randn((B, Cin, H, W), generator=g) * 1.5).cuda(), round_tf32=False)
+    w = ops.prep_weights((torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)).cuda(), cin_pad=Cin)
+    b = torch.randn(Cout, generator=g).cuda()
+    res = ops.to_nhwc(torch.randn((B, Cout, H, W), generator=g).cuda(), round_tf32=False)
+    lib = _lib.load()
+    old = lib.vt_set_option(b"tc_m_major", m_major)
+    ops.set_precision("bf16x3")
+    try:
+        kw = dict(bias=b, act=_lib.ACT_LRELU, slope=0.2, gain=1.0, res=res, alpha=0.7, beta=0.7)
+        y0 = ops.conv2d_nhwc([x], w, ops.conv_taps(k, pad, dil), 1, H, W, **kw)
+        y, st = ops.conv2d_nhwc([x], w, ops.conv_taps(k, pad, dil), 1, H, W, want_stats=True, **kw)
+        assert torch.equal(y, y0)
+        ref = ops.instnorm_stats(y)
+        assert tuple(st.shape) == (B, Cout, 2)
+        assert (st[:, :, 0] - ref[:, :, 0]).abs().max().item() <= 2e-6 * max(1.0, ref[:, :, 0].abs().max().item())
+        assert ((st[:, :, 1] - ref[:, :, 1]) / ref[:, :, 1]).abs().max().item() <= 1e-5
+        yc = ops.to_nchw(y).double()
+        assert (st[:, :, 0].double() - yc.mean(dim=(2, 3))).abs().max().item() <= 1e-5
+        _, st1 = ops.conv2d_nhwc([x[:1].contiguous()], w, ops.conv_taps(k, pad, dil), 1, H, W, want_stats=True,
+                                 **{**kw, "res": res[:1].contiguous()})
+        assert torch.equal(st1, st[:1]), "statistics of a sample depend on its batch"
+        ops.set_option("fuse_stats", False)
+        _, st2 = ops.conv2d_nhwc([x], w, ops.conv_taps(k, pad, dil), 1, H, W, want_stats=True, **kw)
+        assert torch.equal(st2, ref)
+    finally:
+        ops.set_option("fuse_stats", True)
+        lib.vt_set_option(b"tc_m_major", old)
+        ops.set_precision(ops.DEFAULT_PRECISION)

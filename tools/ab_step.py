@@ -9,7 +9,7 @@ from vtoonify_b200.weights import det_inputs, det_state_dict
 
 lib = _lib.load()
 dev = torch.device("cuda:0")
-BASE = {b"tc_stage_policy": 1, b"tc_halo_pct": 60, b"rsu_epi": 1, b"instnorm_chunks": 296, b"tc_warp_store": int(os.environ.get("VT_TC_WARP_STORE", "1")), b"rsu_bstages": 6}
+BASE = {b"tc_stage_policy": 1, b"tc_halo_pct": 60, b"rsu_epi": 1, b"instnorm_chunks": 296, b"tc_warp_store": int(os.environ.get("VT_TC_WARP_STORE", "1")), b"rsu_bstages": 6, b"tc_m_major": 1, "fuse_stats": True}
 CONFIGS = {
     "new (all on)": {},
     "stage_policy 0": {b"tc_stage_policy": 0},
@@ -18,7 +18,9 @@ CONFIGS = {
     "instnorm small chunks": {b"instnorm_chunks": 0},
     "warp_store 0": {b"tc_warp_store": 0},
     "rsu_bstages 4": {b"rsu_bstages": 4},
-    "old (all off)": {b"rsu_bstages": 4, b"tc_stage_policy": 0, b"tc_halo_pct": 50, b"rsu_epi": 0, b"instnorm_chunks": 0, b"tc_warp_store": 0},
+    "tc_m_major 0": {b"tc_m_major": 0},
+    "fuse_stats off": {"fuse_stats": False},
+    "old (all off)": {b"rsu_bstages": 4, b"tc_m_major": 0, "fuse_stats": False, b"tc_stage_policy": 0, b"tc_halo_pct": 50, b"rsu_epi": 0, b"instnorm_chunks": 0, b"tc_warp_store": 0},
 }
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 with torch.no_grad():
@@ -31,7 +33,10 @@ with torch.no_grad():
     for r in range(rounds):
         for name, over in CONFIGS.items():
             for k, v in {**BASE, **over}.items():
-                lib.vt_set_option(k, v)
+                if isinstance(k, bytes):
+                    lib.vt_set_option(k, v)
+                else:
+                    ops.set_option(k, v)          # Python-level routing switches
             for _ in range(2):
                 y = m(x, s, d_s=0.5).clamp_(-1, 1)
             torch.cuda.synchronize()

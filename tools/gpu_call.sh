@@ -1,4 +1,8 @@
-# scratch driver for one gpurun call (edited per call): 2-GPU checks
+# scratch driver for one gpurun call (edited per call)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_dist.py -x -q -m gpu > gpurun_out/g2_dist_test.log 2>&1; tail -n 3 gpurun_out/g2_dist_test.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/g2_bench_2gpu.json 2> gpurun_out/g2_bench_2gpu.err; tail -c 400 gpurun_out/g2_bench_2gpu.json
+timeout 300 python -m pytest tests/test_gpu_conv.py -x -q -m gpu -k "fused_output_statistics or scheduling_options or instnorm_chunk" > gpurun_out/d6_new_tests.log 2>&1
+RC=$?
+tail -n 4 gpurun_out/d6_new_tests.log
+if [ $RC -ne 0 ]; then echo "NEW TESTS FAILED rc=$RC"; grep -n "Error\|assert" gpurun_out/d6_new_tests.log | head -20; fi
+(time timeout 1200 python -m pytest tests/ -x -q -m gpu) > gpurun_out/d6_pytest.log 2>&1; tail -n 8 gpurun_out/d6_pytest.log
+timeout 300 python tools/ab_step.py 3 > gpurun_out/d6_ab.log 2>&1; tail -n 14 gpurun_out/d6_ab.log

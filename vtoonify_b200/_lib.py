@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvtoonify_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 VT_MAX_TAPS = 36
 ACT_NONE, ACT_LRELU, ACT_RELU_TANH = 0, 1, 2
 
@@ -37,6 +37,7 @@ class ConvDesc(Structure):
         ("rgb_out", c_void_p),
         ("slope_vec", c_void_p), ("weight_bf16x3", c_void_p), ("bf16x3_nstack", c_int32), ("reserved2", c_int32), ("src_scale", c_void_p * 2), ("src_affine", c_void_p * 2),
         ("split_fmt", c_int32), ("acc_scale", c_float),
+        ("stats_ws", c_void_p), ("stats_ws_floats", c_int64),
     ]
 
 
@@ -93,6 +94,8 @@ SYMBOLS = {
     "vt_fir_nhwc_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int,
                                 c_float, c_float, c_int, _P]),
     "vt_instnorm_ws_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),
+    "vt_instnorm_finalize_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_float, _P]),
+    "vt_conv2d_tc_stats_chunks": (c_int, [POINTER(ConvDesc)]),
     "vt_instnorm_stats_nhwc": (c_int, [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, _P, _P, _P]),
     "vt_frame_s2d_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vt_maxpool3x3s2_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -130,7 +133,7 @@ def load():
     if lib.vt_abi_version() != ABI_VERSION:
         raise VtError(f"ABI mismatch: library reports {lib.vt_abi_version()}, binding expects {ABI_VERSION}")
     for env, key in (("VT_TC_MODE", b"tc_mode"), ("VT_TC_MT", b"tc_mt"), ("VT_TC_TGROUP", b"tc_tgroup"), ("VT_TC_CG2", b"tc_cg2"),
-                     ("VT_TC_DIRECT_STORE", b"tc_direct_store"), ("VT_TC_STRICT", b"tc_strict"), ("VT_TC_STAGE_POLICY", b"tc_stage_policy"), ("VT_TC_HALO_PCT", b"tc_halo_pct"), ("VT_RS_STRICT", b"rs_strict"), ("VT_RSU_EPI", b"rsu_epi"), ("VT_TC_WARP_STORE", b"tc_warp_store"),
+                     ("VT_TC_DIRECT_STORE", b"tc_direct_store"), ("VT_TC_STRICT", b"tc_strict"), ("VT_TC_STAGE_POLICY", b"tc_stage_policy"), ("VT_TC_HALO_PCT", b"tc_halo_pct"), ("VT_RS_STRICT", b"rs_strict"), ("VT_RSU_EPI", b"rsu_epi"), ("VT_TC_WARP_STORE", b"tc_warp_store"), ("VT_TC_M_MAJOR", b"tc_m_major"),
                      ("VT_INSTNORM_CHUNKS", b"instnorm_chunks")):
         if os.environ.get(env) is not None and os.environ.get(env) != "":
             lib.vt_set_option(key, int(os.environ[env]))      # tuning experiments only

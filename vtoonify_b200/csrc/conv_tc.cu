@@ -80,6 +80,10 @@ struct TcArgs {
   int in_w, in_h;            // kernel-space input extents
   int mma_n;                 // N of one MMA / TMEM columns per accumulator: block_n, or 2*block_n in the N-stacked bf16x3 form
   int nstack;                // bf16x3, Cout == 32: weight rows [w_hi|w_hi] x32 then [w_lo|w_lo] x32 -> 4 MMAs per tap, halves summed in the epilogue
+  int m_major;               // work-item order: the N tiles of one pixel tile are neighbours (run on neighbouring CTA pairs at the
+                             // same time, so the second read of the activations hits L2) instead of N-tile-major
+  float* stats_ws;           // optional instance-norm partial sums of the OUTPUT: [chunk][B][Cout][2] (sum, sum of squares), one chunk per
+                             // (pixel tile, epilogue warp); finalised by vt_instnorm_finalize_f32
   int warp_store;            // epilogue: every warp stages and TMA-stores its own 32 pixels (8 x 4 box), no CTA-wide barrier
   int direct_store;          // epilogue writes its 128-byte pixel rows straight to global memory instead of smem staging + TMA store
   int pair_y;                // CG == 2: the CTA pair is stacked along y (rows) instead of x
@@ -165,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     int a_st = 0, b_st = 0;
     uint32_t a_par = 0, b_par = 0;
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
-      const int n_tile = tile / m_tiles, m = tile % m_tiles;
+      const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles, m = p.m_major ? tile / p.n_tiles : tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
       const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
@@ -339,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     uint32_t a_par = 0;
     const int bw = p.halo ? p.halo_w : TILE_W;   // pixels per box row
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
-      const int m = tile % m_tiles;
+      const int m = p.m_major ? tile / p.n_tiles : tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
       const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       for (int s = 0; s < p.n_src; ++s) {
@@ -424,7 +428,7 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
     int as = 0;
     uint32_t t_par = 0;
     for (int tile = cta_i; tile < p.total_tiles; tile += cta_n) {
-      const int n_tile = tile / m_tiles, m = tile % m_tiles;
+      const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_tiles, m = p.m_major ? tile / p.n_tiles : tile % m_tiles;
       const int b = m / tiles_per_img, rem = m % tiles_per_img;
       const int oy0 = (rem / p.tiles_x) * item_h + rank_y, ox0 = (rem % p.tiles_x) * item_w + rank_x;
       const int n0 = n_tile * p.block_n;
@@ -579,6 +583,23 @@ conv_tc_kernel(const __grid_constant__ TcArgs p) {
               tma_store_4d(&p.out_map[ph], sbuf + (uint32_t)q * 4096u, nb, ox0 + g * TILE_W, oy0 + q * 4, b);
               tma_store_commit();
             }
+            if (p.stats_ws) {
+              // AdaptiveInstanceNorm statistics of the tensor this launch writes (model/dualstylegan.py:10-21), taken from the staged
+              // values: lane c adds channel nb + c over the warp's 32 pixels in row order (fixed order, no atomics), rows outside
+              // the image masked.  Word c of row rr sits in 16-byte chunk (c / 4) ^ (rr & 7): 32 distinct banks per read.
+              const unsigned okm = __ballot_sync(0xffffffffu, in_img);
+              float ssum = 0.f, ssq = 0.f;
+              const uint32_t wbase = sbuf + (uint32_t)q * 4096u + (uint32_t)((lane & 3) << 2);
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                float xv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(wbase + (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7))) << 4)));
+                if ((okm >> rr) & 1u) { ssum += xv; ssq = fmaf(xv, xv, ssq); }
+              }
+              const int kchunk = (((rem * CG + (int)rank) * p.mt + g) << 2) + q;
+              float2* wsp = reinterpret_cast<float2*>(p.stats_ws) + ((int64_t)kchunk * p.B + b) * p.Cout + nb + lane;
+              *wsp = make_float2(ssum, ssq);
+            }
           } else {
             named_bar_sync(1, 128);
             if (store_thread) {
@@ -705,6 +726,7 @@ int g_tc_tgroup = 0;  // 0: automatic taps per weight box (<= 36 KB); 1: one tap
 int g_tc_s2_halo = 0;  // 1: stride-2 layers may use halo staging (4 parity-view boxes per K chunk, 78 KB for a 3x3) and with it CTA pairs
 int g_tc_stage_policy = 1;  // big halo boxes (dilated 3x3): 0 = shrink the weight ring first (3 + 3 stages at dilation 4), 1 = keep >= 5 weight stages and drop to 2 halo stages
 int g_tc_halo_pct = 60;    // halo staging must stage at most this percentage of the per-tap bytes (stride 1)
+int g_tc_m_major = 1;      // work items ordered pixel-tile-major (the N tiles of a pixel tile run side by side: the activations' second read hits L2)
 int g_tc_warp_store = 1;   // epilogue: per-warp staging + TMA stores (8 x 4 pixel boxes) instead of one CTA-wide store per chunk
 int g_tc_strict = 1;  // 1: cluster-scope release arrive in the transform warps (no measurable cost here: 74.43 vs 74.41 frames/s); 0: plain remote arrive
 
@@ -752,6 +774,7 @@ extern "C" int vt_set_option(const char* key, int value) {
   if (key && strcmp(key, "tc_s2_halo") == 0) { int old = g_tc_s2_halo; g_tc_s2_halo = value; return old; }
   if (key && strcmp(key, "tc_stage_policy") == 0) { int old = g_tc_stage_policy; g_tc_stage_policy = value; return old; }
   if (key && strcmp(key, "tc_halo_pct") == 0) { int old = g_tc_halo_pct; g_tc_halo_pct = value; return old; }
+  if (key && strcmp(key, "tc_m_major") == 0) { int old = g_tc_m_major; g_tc_m_major = value; return old; }
   if (key && strcmp(key, "tc_warp_store") == 0) { int old = g_tc_warp_store; g_tc_warp_store = value; return old; }
   if (key && strcmp(key, "tc_strict") == 0) { int old = g_tc_strict; g_tc_strict = value; return old; }
   if (key && strcmp(key, "tc_direct_store") == 0) { int old = g_tc_direct_store; g_tc_direct_store = value; return old; }
@@ -773,7 +796,8 @@ extern "C" int vt_conv2d_tc_supported(const vt_conv_desc* d) {
   return check_supported(d, false);
 }
 
-extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
+// chunks_out != NULL: plan only — how many instance-norm partial-sum chunks this descriptor's launch writes per (sample, channel)
+static int conv_tc_run(const vt_conv_desc* d, void* stream, int* chunks_out) {
   if (vt_validate_conv_desc(d, "conv2d_tc")) return 1;
   if (!check_supported(d, true)) return 1;
 
@@ -972,6 +996,25 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   const int64_t total = (int64_t)a.n_tiles * a.B * a.tiles_x * a.tiles_y;
   VT_CHECK(total < (1LL << 31), "conv_tc: too many tiles");
   a.total_tiles = (int)total;
+  a.m_major = g_tc_m_major ? 1 : 0;
+  {
+    // fused instance-norm statistics of the output: one chunk per (pixel tile of an image, epilogue warp)
+    const int64_t chunks = (int64_t)a.tiles_x * a.tiles_y * cg * mt * 4;
+    if (chunks_out) {
+      VT_CHECK(a.warp_store && !a.direct_store && d->n_phase == 1 && !d->rgb_w && chunks < (1 << 24),
+               "conv_tc: output statistics need the per-warp store epilogue, one phase and no fused ToRGB");
+      *chunks_out = (int)chunks;
+      return 0;
+    }
+    if (d->stats_ws) {
+      VT_CHECK(a.warp_store && !a.direct_store && d->n_phase == 1 && !d->rgb_w,
+               "conv_tc: output statistics need the per-warp store epilogue, one phase and no fused ToRGB");
+      VT_CHECK(d->stats_ws_floats >= chunks * d->B * d->Cout * 2, "conv_tc: stats_ws too small (%lld floats, need %lld)",
+               (long long)d->stats_ws_floats, (long long)(chunks * d->B * d->Cout * 2));
+      VT_CHECK(((uintptr_t)d->stats_ws & 7) == 0, "conv_tc: stats_ws not 8-byte aligned");
+      a.stats_ws = d->stats_ws;
+    }
+  }
 
   // ---- tensor maps (dims innermost first: channels, kernel-x, kernel-y, batch)
   for (int s = 0; s < d->n_src; ++s) {
@@ -1053,6 +1096,14 @@ extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) {
   }
   VT_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int vt_conv2d_tc_tf32(const vt_conv_desc* d, void* stream) { return conv_tc_run(d, stream, nullptr); }
+
+extern "C" int vt_conv2d_tc_stats_chunks(const vt_conv_desc* d) {
+  int chunks = 0;
+  if (conv_tc_run(d, nullptr, &chunks)) return -1;
+  return chunks;
 }
 
 // ---- tcgen05 issue-rate microbenchmark (tuning aid, tests/ and tools/ only) -----------------------------------------

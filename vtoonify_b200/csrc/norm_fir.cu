@@ -367,6 +367,14 @@ extern "C" int vt_instnorm_stats_nhwc(const float* in, const float* in2, int mod
   return 0;
 }
 
+extern "C" int vt_instnorm_finalize_f32(const float* ws, float* stats, int B, int Cs, int chunks, int64_t HW, float eps, void* stream) {
+  VT_CHECK(ws && stats && B >= 1 && Cs >= 1 && chunks >= 1 && HW >= 1, "instnorm_finalize: bad args");
+  const int n = B * Cs;
+  instnorm_finalize_kernel<<<(unsigned)vt_cdiv(n, 32), 256, 0, (cudaStream_t)stream>>>(ws, stats, n, chunks, 1.0 / (double)HW, eps);
+  VT_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void adain_affine_kernel(const float* __restrict__ stats, const float* __restrict__ gb, float* __restrict__ aff, int B, int Cs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = b * Cs + c
   if (i >= B * Cs) return;

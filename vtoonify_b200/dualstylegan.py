@@ -47,9 +47,10 @@ class AdaptiveInstanceNorm(nn.Module):
         stats = ops.instnorm_stats(x, x2)
         return ops.adain_apply(x, stats, gb, x2)
 
-    def affine(self, x, style):
-        """The same AdaIN as a [B, C, 2] (scale, shift) table for a convolution that applies it to its input on the fly."""
-        return ops.adain_affine(ops.instnorm_stats(x), self.gamma_beta(style, x.shape[0]))
+    def affine(self, x, style, stats=None):
+        """The same AdaIN as a [B, C, 2] (scale, shift) table for a convolution that applies it to its input on the fly.
+        ``stats``: (mean, rstd) of ``x`` when the kernel that produced ``x`` already delivered them."""
+        return ops.adain_affine(ops.instnorm_stats(x) if stats is None else stats, self.gamma_beta(style, x.shape[0]))
 
     def forward(self, input, style):
         return ops.nhwc_as_nchw_view(self.forward_nhwc(ops.to_nhwc(input), style))
@@ -67,14 +68,16 @@ class AdaResBlock(nn.Module):
         self.conv[0].weight.data *= 0.01
         self.conv2[0].weight.data *= 0.01
 
-    def forward_nhwc(self, x, s, w=1):
+    def forward_nhwc(self, x, s, w=1, x_stats=None):
+        """``x_stats``: instance-norm statistics of ``x`` from the kernel that produced it (else a statistics pass runs)."""
         if w == 0:
             return x
         if ops.affine_fusable():
             # the normalised tensors are never written: each conv applies its AdaIN (scale, shift per sample and channel) to
-            # the pixels it stages, padding stays zero as in the reference (which zero-pads the normalised tensor)
-            out = self.conv.forward_nhwc(x, src_affine=self.norm.affine(x, s))
-            return self.conv2.forward_nhwc(out, src_affine=self.norm2.affine(out, s), res=x, alpha=float(w), beta=1.0)
+            # the pixels it stages, padding stays zero as in the reference (which zero-pads the normalised tensor); the
+            # statistics of conv's output come out of conv's own epilogue
+            out, st = self.conv.forward_nhwc(x, src_affine=self.norm.affine(x, s, x_stats), want_stats=True)
+            return self.conv2.forward_nhwc(out, src_affine=self.norm2.affine(out, s, st), res=x, alpha=float(w), beta=1.0)
         out = self.conv.forward_nhwc(self.norm.forward_nhwc(x, s))
         return self.conv2.forward_nhwc(self.norm2.forward_nhwc(out, s), res=x, alpha=float(w), beta=1.0)
 

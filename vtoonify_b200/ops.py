@@ -49,7 +49,10 @@ _options = {"fold_upconv": 128, "fuse_torgb": True, "fuse_mask_mul": True, "smal
             "rs_conv": True, "rs_min_width": 256, "rs_fmt": _os.environ.get("VT_SPLIT_FMT", "bf16"), "nvtx": bool(_os.environ.get("VT_NVTX")),
             # rsu_conv: up-convolutions with Cin <= rsu_max_cin and rows of >= rs_min_width pixels on the row-strip up-conv kernel
             # (horizontal blur folded into the weights, vertical blur on the TMEM accumulators: conv_rsu.cu)
-            "rsu_conv": True, "rsu_max_cin": 128}
+            "rsu_conv": True, "rsu_max_cin": 128,
+            # fuse_stats: AdaIN statistics of a conv output come from the producing kernel's epilogue (per-tile partial sums + finalize)
+            # instead of a separate pass over the tensor
+            "fuse_stats": True}
 if _os.environ.get("VT_FOLD_UPCONV_MAX_CIN"):
     _options["fold_upconv"] = int(_os.environ["VT_FOLD_UPCONV_MAX_CIN"])
 if _os.environ.get("VT_RSU_MAX_CIN"):
@@ -393,8 +396,12 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 res: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
                 precision: Optional[str] = None, rgb: Optional[dict] = None,
                 slope_vec: Optional[torch.Tensor] = None, src_scale: Optional[Sequence] = None,
-                src_affine: Optional[Sequence] = None) -> torch.Tensor:
+                src_affine: Optional[Sequence] = None, want_stats: bool = False, stats_eps: float = 1e-5) -> torch.Tensor:
     """General NHWC convolution (virtual channel-concat of ``srcs``).
+
+    ``want_stats``: also return the instance-norm statistics ``[B, Cout, 2]`` = (mean, rstd) of the OUTPUT (what
+    :func:`instnorm_stats` would compute from it): the tensor-core kernel's epilogue warps write per-tile partial sums of the values
+    they store and only the finalize pass runs afterwards; other routes fall back to the separate statistics pass.
 
     ``weight``: ``[wB, w_taps, Cout, w_cstride]`` from :func:`prep_weights`.
     ``out_view``: (offset_elems, sb, sy, sx) strided view into ``out`` (used for polyphase transposed conv).
@@ -504,6 +511,8 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
                 _tc_profile.append((e0, e1, flops, nbytes, f"{cin}->{Cout} k9 s1 {H}x{W} [row-strip{'' if out is not None else ', image only'}]", 3.0 * flops))
             else:
                 check(lib.vt_conv2d_rs(d, acc_scale, _stream()))
+            if want_stats:
+                return out, instnorm_stats(out, eps=stats_eps)
             return out if rgb is None else (out, rgb_out)
         d.weight_bf16x3 = None
         d.bf16x3_nstack = 0
@@ -525,6 +534,14 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
         else:
             d.weight_bf16x3 = split_weights_bf16x3(weight, nstack).data_ptr()
             d.bf16x3_nstack = 1 if nstack else 0
+    stats = stats_ws = None
+    if want_stats:
+        if rgb is not None or out_view is not None or phase_offs is not None:
+            raise _lib.VtError("conv2d_nhwc: want_stats needs a dense single-phase output without the fused ToRGB tail")
+        chunks = lib.vt_conv2d_tc_stats_chunks(d) if (use_tc and _options["fuse_stats"]) else -1
+        if chunks > 0:
+            stats_ws = torch.empty((chunks * B * Cout * 2,), device=out.device, dtype=torch.float32)
+            d.stats_ws, d.stats_ws_floats = stats_ws.data_ptr(), stats_ws.numel()
     if use_tc:
         if _tc_profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -542,6 +559,13 @@ def conv2d_nhwc(srcs: Sequence[torch.Tensor], weight: torch.Tensor, taps, stride
             check(lib.vt_conv2d_tc_tf32(d, _stream()))
     else:
         check(lib.vt_conv2d_direct_f32(d, _stream()))
+    if want_stats:
+        if stats_ws is not None:
+            stats = torch.empty((B, Cout, 2), device=out.device, dtype=torch.float32)
+            check(lib.vt_instnorm_finalize_f32(stats_ws.data_ptr(), stats.data_ptr(), B, Cout, chunks, Ho * Wo, stats_eps, _stream()))
+        else:
+            stats = instnorm_stats(out, eps=stats_eps)
+        return out, stats
     return out if rgb is None else (out, rgb_out)
 
 

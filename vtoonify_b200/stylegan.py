@@ -99,8 +99,9 @@ class _PreppedWeight:
 
 
 def _conv_plain_nhwc(x, weight, wcache, scale, bias, stride, padding, dilation, act=ACT_NONE, slope=0.2, gain=1.0,
-                     res=None, alpha=1.0, beta=1.0, src_affine=None):
-    """Shared body of EqualConv2d / Conv2d on an NHWC tensor."""
+                     res=None, alpha=1.0, beta=1.0, src_affine=None, want_stats=False):
+    """Shared body of EqualConv2d / Conv2d on an NHWC tensor.  ``want_stats``: returns ``(out, stats)`` with the instance-norm
+    statistics of the output (ops.conv2d_nhwc)."""
     B, H, W, Cs = x.shape
     Cout, Cin, k, _ = weight.shape
     w = wcache.get(weight, scale, Cs)
@@ -108,7 +109,7 @@ def _conv_plain_nhwc(x, weight, wcache, scale, bias, stride, padding, dilation, 
     Wo = ops.conv_out_size(W, k, stride, padding, dilation)
     return ops.conv2d_nhwc([x], w, ops.conv_taps(k, padding, dilation), stride, Ho, Wo, bias=bias, act=act, slope=slope,
                            gain=gain, res=res, alpha=alpha, beta=beta,
-                           src_affine=None if src_affine is None else [src_affine])
+                           src_affine=None if src_affine is None else [src_affine], want_stats=want_stats)
 
 
 class EqualConv2d(nn.Module):
@@ -482,9 +483,9 @@ class ConvLayer(nn.Sequential):
             layers.append(FusedLeakyReLU(out_channel, bias=bias))
         super().__init__(*layers)
 
-    def forward_nhwc(self, x, res=None, alpha=1.0, beta=1.0, src_affine=None):
+    def forward_nhwc(self, x, res=None, alpha=1.0, beta=1.0, src_affine=None, want_stats=False):
         """Fused conv + FusedLeakyReLU (+ ``v*alpha + beta*res``) for the non-downsampling form; ``src_affine``: AdaIN table
-        applied to the input inside the convolution."""
+        applied to the input inside the convolution; ``want_stats``: ``(out, instance-norm statistics of out)``."""
         mods = list(self)
         if isinstance(mods[0], Blur):
             raise NotImplementedError("ConvLayer(downsample=True) is discriminator-only (training)")
@@ -492,5 +493,5 @@ class ConvLayer(nn.Sequential):
         if len(mods) > 1:
             act = mods[1]
             return conv.forward_nhwc(x, bias=act.bias, act=ACT_LRELU, slope=act.negative_slope, gain=act.scale,
-                                     res=res, alpha=alpha, beta=beta, src_affine=src_affine)
-        return conv.forward_nhwc(x, res=res, alpha=alpha, beta=beta, src_affine=src_affine)
+                                     res=res, alpha=alpha, beta=beta, src_affine=src_affine, want_stats=want_stats)
+        return conv.forward_nhwc(x, res=res, alpha=alpha, beta=beta, src_affine=src_affine, want_stats=want_stats)

@@ -38,8 +38,10 @@ class Conv2d(nn.Module):
         self._w = _PreppedWeight()
         self._wp = _PreppedWeight()
 
-    def forward_nhwc(self, x, act=ACT_NONE, slope=0.2, gain=1.0, res=None, alpha=1.0, beta=1.0, x2=None, x2_scale=None):
-        """x (and optional second concat source x2, optionally multiplied per pixel by the planar map x2_scale) NHWC -> NHWC."""
+    def forward_nhwc(self, x, act=ACT_NONE, slope=0.2, gain=1.0, res=None, alpha=1.0, beta=1.0, x2=None, x2_scale=None,
+                     want_stats=False):
+        """x (and optional second concat source x2, optionally multiplied per pixel by the planar map x2_scale) NHWC -> NHWC;
+        ``want_stats``: ``(out, instance-norm statistics of out)`` (ops.conv2d_nhwc)."""
         B, H, W, Cs = x.shape
         k = self.kernel_size
         cin = Cs + (0 if x2 is None else x2.shape[3])
@@ -49,7 +51,7 @@ class Conv2d(nn.Module):
         srcs = [x] if x2 is None else [x, x2]
         return ops.conv2d_nhwc(srcs, w, ops.conv_taps(k, self.padding), self.stride, Ho, Wo, bias=self.bias, act=act,
                                slope=slope, gain=gain, res=res, alpha=alpha, beta=beta,
-                               src_scale=None if x2_scale is None else [None, x2_scale])
+                               src_scale=None if x2_scale is None else [None, x2_scale], want_stats=want_stats)
 
     def forward_smalln(self, x, planar=None, act=ACT_NONE, mul_src=None, src_mask=None):
         """Cout <= 4 form: input channels = [planar (NCHW, first) | x (NHWC)] -> planar NCHW output."""
@@ -125,10 +127,12 @@ class VToonifyResBlock(nn.Module):
         self.conv2 = Conv2d(fin, fin, 3, 1, 1)
         self.lrelu = LeakyReLU(negative_slope=0.2, inplace=True)
 
-    def forward_nhwc(self, x):
+    def forward_nhwc(self, x, want_stats=False):
+        """``want_stats``: ``(out, instance-norm statistics of out)`` for an AdaIN consumer (the dilated ModRes block that follows
+        every encoder res block in VToonify-D, model/vtoonify.py:239)."""
         out = self.conv.forward_nhwc(x, act=ACT_LRELU, slope=0.2, gain=1.0)
         r = 1.0 / math.sqrt(2)
-        return self.conv2.forward_nhwc(out, act=ACT_LRELU, slope=0.2, gain=1.0, res=x, alpha=r, beta=r)
+        return self.conv2.forward_nhwc(out, act=ACT_LRELU, slope=0.2, gain=1.0, res=x, alpha=r, beta=r, want_stats=want_stats)
 
     def forward(self, x):
         return ops.nhwc_as_nchw_view(self.forward_nhwc(ops.to_nhwc(x)))
@@ -265,9 +269,13 @@ class VToonify(ops.WeightsEpochMixin, nn.Module):
         encoder_features = encoder_features[::-1]
         for ii, block in enumerate(self.encoder[-2]):
             with ops.nvtx_range(f"vtoonify/resblock.{ii}"):
-                feat = block.forward_nhwc(feat)
-                if D:
-                    feat = self.res[ii + 1].forward_nhwc(feat, resstyles[:, ii + 1], d_s)
+                if D and ops.affine_fusable():
+                    feat, st = block.forward_nhwc(feat, want_stats=True)
+                    feat = self.res[ii + 1].forward_nhwc(feat, resstyles[:, ii + 1], d_s, x_stats=st)
+                else:
+                    feat = block.forward_nhwc(feat)
+                    if D:
+                        feat = self.res[ii + 1].forward_nhwc(feat, resstyles[:, ii + 1], d_s)
         out = feat
         skip = self.encoder[-1].forward_smalln(feat)
         if return_feat:

@@ -13,12 +13,14 @@
 // One MMA per (input row i, dx = dj, 32-channel chunk, product):  D[128 px of row i, (ky, px, co)] += X[row i, px+dj] * Gx,
 // N = 3 * 2 * 32 = 192: an input row adds into the three tx rows 2i, 2i+1, 2i+2, which are slots of a TMEM ring (64 columns
 // each: [px=0 | px=1] x 32 output channels; slot of row p = (p + 2) mod 6, one mirror slot behind the ring keeps every window
-// contiguous).  The MMAs always accumulate; the epilogue forms each output row as the 4-tap vertical blur of four finished tx
-// rows (TMEM -> registers), applies noise / bias / leaky-relu, writes the two interleaved pixel phases through a swizzled staging
-// tile + TMA store, and zeroes a tx row once the last output row that needs it has been produced.  The slot of a row depends on
+// contiguous).  The MMAs always accumulate; the epilogue forms the two output rows of an input row as 4-tap vertical blurs of five
+// finished tx rows (TMEM -> registers, one pass per pixel phase, the two dying rows first), applies noise / bias / leaky-relu, writes
+// the two interleaved pixel phases through a swizzled staging tile + TMA store, and zeroes a tx row once it has been read for the
+// last time (its slot is what the MMA issuer's next input row is waiting for).  The slot of a row depends on
 // its image row only, so results do not depend on the strip partition or the batch composition.
 // A launch produces 32 output channels; Cout = 64 is two passes over the input (the second reads it from L2 / HBM again).
-// Weight tiles (12 KB per (chunk, dx)) stream through a 4-deep ring like the activations: Cin = 128 needs 144 KB of them per row.
+// Weight tiles (12 KB per (chunk, dx) and CTA of a pair) stream through a 6-deep ring like the activations (Cin = 128 needs 144 KB of
+// them per row; at Cin = 64 the ring holds a whole row's tiles).
 // Roles (10 warps): 0 TMA producer | 1 MMA issuer | 2,3,8,9 operand transform | 4-7 epilogue.
 #include "tc_common.cuh"
 #include <cuda_bf16.h>

@@ -87,3 +87,40 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.VtError, match="no CPU"):
         _lib.load()
+
+
+def _plan_desc(B, Cin, Cout, H, W, k=3, dil=1):
+    """A descriptor with placeholder (aligned, never dereferenced) pointers: planning calls launch nothing."""
+    from vtoonify_b200 import _lib
+    d = _lib.ConvDesc()
+    d.struct_size = ctypes.sizeof(_lib.ConvDesc)
+    d.n_src = 1
+    d.src[0] = 0x10000
+    d.src_c[0] = d.src_cstride[0] = Cin
+    d.B, d.H, d.W, d.Ho, d.Wo = B, H, W, H, W
+    d.stride, d.taps = 1, k * k
+    for t in range(k * k):
+        d.tap_dy[t], d.tap_dx[t], d.tap_w[t] = (t // k - k // 2) * dil, (t % k - k // 2) * dil, t
+    d.n_phase, d.out_cpitch = 1, Cout
+    d.weight, d.weight_bf16x3 = 0x20000, 0x40000
+    d.wB, d.w_taps, d.w_cstride, d.Cout = 1, k * k, Cin, Cout
+    d.out = 0x30000
+    d.out_sb, d.out_sy, d.out_sx = H * W * Cout, W * Cout, Cout
+    d.alpha = d.beta = 1.0
+    return d
+
+
+def test_output_statistics_plan_is_host_only_and_batch_independent():
+    """vt_conv2d_tc_stats_chunks plans without touching the GPU: one chunk per (pixel tile of an image, CTA of a pair, M tile of
+    the work item, epilogue warp); the plan must not depend on the batch size (a frame's statistics may not depend on its batch)."""
+    from vtoonify_b200 import _lib
+    lib = _lib.load()
+    # 72 x 128 maps are handed over transposed: 9 x 8 tiles of 8 x 16 pixels = 36 pair items x 2 CTAs x 4 warps
+    assert lib.vt_conv2d_tc_stats_chunks(ctypes.byref(_plan_desc(4, 512, 512, 72, 128))) == 288
+    for shape in [(512, 512, 72, 128, 3, 1), (512, 512, 72, 128, 3, 4), (64, 128, 19, 45, 3, 1), (128, 32, 16, 24, 1, 1), (32, 64, 9, 7, 3, 1)]:
+        n = [lib.vt_conv2d_tc_stats_chunks(ctypes.byref(_plan_desc(B, *shape))) for B in (1, 2, 4, 7)]
+        assert n[0] > 0 and len(set(n)) == 1, (shape, n)
+    d = _plan_desc(1, 64, 128, 16, 16)
+    d.n_phase = 4                                   # folded up-conv phases cannot deliver statistics
+    d.Cout = 32
+    assert lib.vt_conv2d_tc_stats_chunks(ctypes.byref(d)) == -1 and lib.vt_last_error()
